@@ -1,0 +1,34 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_vectors.npz")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(GOLDEN)
+
+
+def has_gpu():
+    """True when a CUDA device is visible (checked without torch: the product path has no torch)."""
+    return os.path.exists("/dev/nvidiactl") or os.path.exists("/dev/nvidia0")
+
+
+def assert_close(got, ref, rtol=1e-9, what=""):
+    """The parity bar of SURVEY.md section 8c: rtol on each element plus a scale-relative atol
+    of rtol * max|ref| (posterior covariances have entries that cancel to ~0)."""
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
+    scale = float(np.max(np.abs(ref))) if ref.size else 1.0
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * max(scale, 1e-300), err_msg=what)
