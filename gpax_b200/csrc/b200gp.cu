@@ -1,0 +1,829 @@
+// b200gp.cu -- C-ABI entry points of libb200gp.so (see include/b200gp.h for the contract and the
+// reference lines each entry point replaces).  Host code here only orchestrates: workspace, streams,
+// the order of kernel launches.  No torch, no JAX, no CPU fallback: every numerical result is
+// produced by the sm_100a kernels in gram.cuh / gemm_dmma.cuh / potrf.cuh / posterior.cuh.
+#include "common.cuh"
+#include "gemm_dmma.cuh"
+#include "gram.cuh"
+#include "posterior.cuh"
+#include "potrf.cuh"
+
+// ------------------------------------------------------------------------------------------ helpers
+namespace {
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t next = 0;
+    cudaEvent_t get() {
+        if (next == ev.size()) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+            ev.push_back(e);
+        }
+        return ev[next++];
+    }
+    void reset() { next = 0; }
+    void destroy() {
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        next = 0;
+    }
+};
+
+struct Extra {  // ctx-private state that is not part of the struct the kernels' headers see
+    EventPool pool;
+    b2gp_timing last{};
+    cudaEvent_t slot_done[B2GP_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t inputs_ready = nullptr;
+    DevBuf theta1;     // one-draw theta for b2gp_gram
+    DevBuf potrf_buf;  // staging for host-pointer b2gp_potrf / trsm / gemm
+    DevBuf gemm_buf[3];
+    std::vector<void*> user_allocs;
+};
+
+}  // namespace
+
+static std::vector<std::pair<b2gp_ctx*, Extra*>> g_extras;
+static Extra* extra_of(b2gp_ctx* ctx) {
+    for (auto& p : g_extras)
+        if (p.first == ctx) return p.second;
+    return nullptr;
+}
+
+static inline bool dev_ptrs(unsigned flags) { return (flags & B2GP_FLAG_DEVICE_PTRS) != 0; }
+
+static int free_buf(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+    return 0;
+}
+
+struct CallTimer {
+    b2gp_ctx* ctx;
+    Extra* ex;
+    int64_t launches0;
+    CallTimer(b2gp_ctx* c) : ctx(c), ex(extra_of(c)), launches0(c->launches) {}
+    int begin(cudaStream_t st) {
+        ex->last = b2gp_timing{};
+        ex->pool.reset();
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_begin, st));
+        return B2GP_OK;
+    }
+    int end(cudaStream_t st, b2gp_timing* out) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_end, st));
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_end));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+        ex->last.total_ms = ms;
+        ex->last.launches = ctx->launches - launches0;
+        if (out) *out = ex->last;
+        return B2GP_OK;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ lifecycle
+extern "C" int b2gp_version(void) { return B2GP_VERSION; }
+
+extern "C" int b2gp_ctx_create(int device, b2gp_ctx** out) {
+    if (!out) return B2GP_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return B2GP_ERR_CUDA;
+    if (device < 0 || device >= ndev) return B2GP_ERR_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return B2GP_ERR_CUDA;
+    b2gp_ctx* ctx = new b2gp_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return B2GP_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->mem_bytes = prop.totalGlobalMem;
+    for (int i = 0; i < B2GP_MAX_STREAMS; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) return B2GP_ERR_CUDA;
+        for (int e = 0; e < 8; ++e) cudaEventCreate(&ctx->slots[i].ev[e]);
+    }
+    cudaEventCreate(&ctx->ev_begin);
+    cudaEventCreate(&ctx->ev_end);
+    cudaEventCreate(&ctx->ev_a);
+    cudaEventCreate(&ctx->ev_b);
+    Extra* ex = new Extra();
+    for (int i = 0; i < B2GP_MAX_STREAMS; ++i) cudaEventCreateWithFlags(&ex->slot_done[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ex->inputs_ready, cudaEventDisableTiming);
+    g_extras.emplace_back(ctx, ex);
+    *out = ctx;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
+    if (!ctx) return B2GP_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    Extra* ex = extra_of(ctx);
+    for (int i = 0; i < B2GP_MAX_STREAMS; ++i) {
+        Slot& s = ctx->slots[i];
+        free_buf(s.A);
+        free_buf(s.Vt);
+        free_buf(s.Linv);
+        free_buf(s.cov);
+        free_buf(s.LinvC);
+        free_buf(s.misc);
+        for (int e = 0; e < 8; ++e) cudaEventDestroy(s.ev[e]);
+        cudaStreamDestroy(s.stream);
+    }
+    for (auto& b : ctx->d_in) free_buf(b);
+    for (auto& b : ctx->d_out) free_buf(b);
+    free_buf(ctx->d_info);
+    free_buf(ctx->last_linv);
+    cudaEventDestroy(ctx->ev_begin);
+    cudaEventDestroy(ctx->ev_end);
+    cudaEventDestroy(ctx->ev_a);
+    cudaEventDestroy(ctx->ev_b);
+    if (ex) {
+        ex->pool.destroy();
+        for (int i = 0; i < B2GP_MAX_STREAMS; ++i) cudaEventDestroy(ex->slot_done[i]);
+        cudaEventDestroy(ex->inputs_ready);
+        free_buf(ex->theta1);
+        free_buf(ex->potrf_buf);
+        for (auto& b : ex->gemm_buf) free_buf(b);
+        for (void* p : ex->user_allocs) cudaFree(p);
+        for (size_t i = 0; i < g_extras.size(); ++i)
+            if (g_extras[i].first == ctx) {
+                g_extras.erase(g_extras.begin() + i);
+                break;
+            }
+        delete ex;
+    }
+    delete ctx;
+    return B2GP_OK;
+}
+
+static std::string g_null_err = "null context";
+extern "C" const char* b2gp_last_error(const b2gp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_null_err.c_str(); }
+
+extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return B2GP_ERR_ARG;
+    if (strcmp(key, "streams") == 0) {
+        ARG_CHECK(ctx, value >= 1 && value <= B2GP_MAX_STREAMS);
+        ctx->n_streams = (int)value;
+        return B2GP_OK;
+    }
+    return set_err(ctx, B2GP_ERR_ARG, "b2gp_set_option", "unknown key", __FILE__, __LINE__);
+}
+
+extern "C" int b2gp_device_info(b2gp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* mem_bytes) {
+    if (!ctx) return B2GP_ERR_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_last_timing(b2gp_ctx* ctx, b2gp_timing* out) {
+    if (!ctx || !out) return B2GP_ERR_ARG;
+    *out = extra_of(ctx)->last;
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ memory
+extern "C" int b2gp_dev_alloc(b2gp_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return set_err(ctx, B2GP_ERR_NOMEM, "cudaMalloc", cudaGetErrorString(e), __FILE__, __LINE__);
+    extra_of(ctx)->user_allocs.push_back(p);
+    *dptr = p;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_dev_free(b2gp_ctx* ctx, void* dptr) {
+    if (!ctx) return B2GP_ERR_ARG;
+    if (!dptr) return B2GP_OK;
+    auto& v = extra_of(ctx)->user_allocs;
+    for (size_t i = 0; i < v.size(); ++i)
+        if (v[i] == dptr) {
+            v.erase(v.begin() + i);
+            CUDA_TRY(ctx, cudaFree(dptr));
+            return B2GP_OK;
+        }
+    return set_err(ctx, B2GP_ERR_ARG, "b2gp_dev_free", "pointer not owned by this ctx", __FILE__, __LINE__);
+}
+
+extern "C" int b2gp_host_alloc(b2gp_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaHostAlloc(hptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_host_free(b2gp_ctx* ctx, void* hptr) {
+    if (!ctx) return B2GP_ERR_ARG;
+    if (hptr) CUDA_TRY(ctx, cudaFreeHost(hptr));
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_h2d(b2gp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return B2GP_OK;
+}
+extern "C" int b2gp_d2h(b2gp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return B2GP_OK;
+}
+extern "C" int b2gp_sync(b2gp_ctx* ctx) {
+    if (!ctx) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CUDA_TRY(ctx, cudaDeviceSynchronize());
+    return B2GP_OK;
+}
+
+// stage a host array on the device (returns the device pointer) or pass a device pointer through
+static int stage_in(b2gp_ctx* ctx, cudaStream_t st, DevBuf& buf, const void* src, size_t bytes, bool is_dev,
+                    const double** out) {
+    if (!src) {
+        *out = nullptr;
+        return B2GP_OK;
+    }
+    if (is_dev) {
+        *out = (const double*)src;
+        return B2GP_OK;
+    }
+    RET_IF(ensure(ctx, buf, bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+    *out = (const double*)buf.p;
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ gram
+extern "C" int b2gp_gram(b2gp_ctx* ctx, int kind, const double* X, int64_t n, const double* Z, int64_t m, int d,
+                         const double* lengthscale, double scale, double period, double diag_add, int same_xz, double* K,
+                         int64_t ldk, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, X && Z && K && lengthscale);
+    ARG_CHECK(ctx, n >= 0 && m >= 0 && d >= 1 && d <= GRAM_MAX_D && ldk >= m);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    // theta of a single "draw": lengthscale (always a host pointer: d values), scale, noise := diag_add, period
+    double th[GRAM_MAX_D + 3];
+    for (int k = 0; k < d; ++k) th[k] = lengthscale[k];
+    th[d] = scale;
+    th[d + 1] = diag_add;
+    th[d + 2] = period;
+    RET_IF(ensure(ctx, ex->theta1, sizeof th));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ex->theta1.p, th, (d + 3) * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));  // th is a stack buffer
+    const bool dev = dev_ptrs(flags);
+    const double *dX, *dZ;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], X, (size_t)n * d * 8, dev, &dX));
+    if (Z == X && !dev)
+        dZ = dX;
+    else
+        RET_IF(stage_in(ctx, st, ctx->d_in[1], Z, (size_t)m * d * 8, dev, &dZ));
+    double* dK = K;
+    int64_t ld = ldk;
+    if (!dev) {
+        ld = round_up(m, 2);
+        RET_IF(ensure(ctx, ctx->d_out[0], (size_t)n * ld * 8));
+        dK = (double*)ctx->d_out[0].p;
+    }
+    const int lower = (flags & B2GP_FLAG_LOWER_ONLY) && same_xz && n == m;
+    if (lower && !dev) CUDA_TRY(ctx, cudaMemsetAsync(dK, 0, (size_t)n * ld * 8, st));
+    RET_IF(launch_gram(ctx, st, kind, dX, n, dZ, m, d, (const double*)ex->theta1.p, 1.0, 0.0, same_xz ? 1 : 0, lower, dK, ld));
+    if (!dev)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ld * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    ex->last.gram_bytes = 8.0 * (double)n * (double)m + 8.0 * (double)(n + m) * d;
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ potrf / trsm / gemm
+extern "C" int b2gp_potrf(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, int* info, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, A && info && n >= 0 && lda >= n);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    *info = 0;
+    if (n == 0) return tm.end(st, nullptr);
+    const bool dev = dev_ptrs(flags);
+    double* dA = A;
+    int64_t ld = lda;
+    if (!dev) {
+        ld = round_up(n, 2);
+        RET_IF(ensure(ctx, ex->potrf_buf, (size_t)n * ld * 8));
+        dA = (double*)ex->potrf_buf.p;
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dA, (size_t)ld * 8, A, (size_t)lda * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+    }
+    RET_IF(ensure(ctx, ctx->last_linv, (size_t)linv_bytes(n)));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_info.p, 0, 8, st));
+    RET_IF(potrf_rec(ctx, st, dA, ld, n, (double*)ctx->last_linv.p, (int*)ctx->d_info.p, 0));
+    ctx->last_n = n;
+    if (!dev) {
+        // copy back only the lower triangle's rows; the strict upper triangle of the caller's array is
+        // preserved by copying row i's first i+1 entries
+        // (one 2-D copy of the full rows followed by a host-side restore would touch the upper part)
+        std::vector<double> tmp;  // not used: rows are copied individually below for n small, else via 2-D copy + fixup
+        // Simple and exact: stage the whole factor on the host in a temporary, then write j <= i.
+        tmp.resize((size_t)n * n);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(tmp.data(), (size_t)n * 8, dA, (size_t)ld * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        for (int64_t i = 0; i < n; ++i) memcpy(A + i * lda, tmp.data() + i * n, (size_t)(i + 1) * 8);
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(info, ctx->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    ex->last.flops = (double)n * (double)n * (double)n / 3.0;
+    ex->last.potrf_ms = ex->last.total_ms;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_trsm_lower(b2gp_ctx* ctx, int64_t n, int64_t nrhs, const double* L, int64_t ldl, double* B, int64_t ldb,
+                               unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, L && B && n >= 0 && nrhs >= 0 && ldl >= n && ldb >= n);
+    if (ctx->last_n != n || !ctx->last_linv.p)
+        return set_err(ctx, B2GP_ERR_ARG, "b2gp_trsm_lower", "call b2gp_potrf on this factor first (same ctx, same n)", __FILE__, __LINE__);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    if (n == 0 || nrhs == 0) return tm.end(st, nullptr);
+    const bool dev = dev_ptrs(flags);
+    const double* dL = L;
+    double* dB = B;
+    int64_t ll = ldl, lb = ldb;
+    if (!dev) {
+        ll = round_up(n, 2);
+        lb = ll;
+        RET_IF(ensure(ctx, ex->gemm_buf[0], (size_t)n * ll * 8));
+        RET_IF(ensure(ctx, ex->gemm_buf[1], (size_t)nrhs * lb * 8));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ex->gemm_buf[0].p, (size_t)ll * 8, L, (size_t)ldl * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(ex->gemm_buf[1].p, (size_t)lb * 8, B, (size_t)ldb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyHostToDevice, st));
+        dL = (const double*)ex->gemm_buf[0].p;
+        dB = (double*)ex->gemm_buf[1].p;
+    }
+    RET_IF(trsm_rec(ctx, st, dB, lb, nrhs, dL, ll, n, (const double*)ctx->last_linv.p));
+    if (!dev)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(B, (size_t)ldb * 8, dB, (size_t)lb * 8, (size_t)n * 8, (size_t)nrhs, cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    ex->last.flops = (double)n * (double)n * (double)nrhs;
+    ex->last.trsm_ms = ex->last.total_ms;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_gemm_nt(b2gp_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, A && B && C && m >= 0 && n >= 0 && k >= 0 && lda >= k && ldb >= k && ldc >= n);
+    ARG_CHECK(ctx, !lower_only || m == n);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const bool dev = dev_ptrs(flags);
+    const double *dA = A, *dB = B;
+    double* dC = C;
+    int64_t la = lda, lb = ldb, lc = ldc;
+    if (!dev) {
+        la = lb = round_up(k > 0 ? k : 1, 2);
+        lc = round_up(n > 0 ? n : 1, 2);
+        RET_IF(ensure(ctx, ex->gemm_buf[0], (size_t)(m + 1) * la * 8));
+        RET_IF(ensure(ctx, ex->gemm_buf[1], (size_t)(n + 1) * lb * 8));
+        RET_IF(ensure(ctx, ex->gemm_buf[2], (size_t)(m + 1) * lc * 8));
+        if (m && k) CUDA_TRY(ctx, cudaMemcpy2DAsync(ex->gemm_buf[0].p, (size_t)la * 8, A, (size_t)lda * 8, (size_t)k * 8, (size_t)m, cudaMemcpyHostToDevice, st));
+        if (n && k) CUDA_TRY(ctx, cudaMemcpy2DAsync(ex->gemm_buf[1].p, (size_t)lb * 8, B, (size_t)ldb * 8, (size_t)k * 8, (size_t)n, cudaMemcpyHostToDevice, st));
+        if (m && n) CUDA_TRY(ctx, cudaMemcpy2DAsync(ex->gemm_buf[2].p, (size_t)lc * 8, C, (size_t)ldc * 8, (size_t)n * 8, (size_t)m, cudaMemcpyHostToDevice, st));
+        dA = (const double*)ex->gemm_buf[0].p;
+        dB = (A == B && lda == ldb && m == n) ? dA : (const double*)ex->gemm_buf[1].p;
+        dC = (double*)ex->gemm_buf[2].p;
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
+    RET_IF(gemm_nt(ctx, st, m, n, k, alpha, dA, la, dB, lb, beta, dC, lc, lower_only != 0));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
+    if (!dev && m && n)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(C, (size_t)ldc * 8, dC, (size_t)lc * 8, (size_t)n * 8, (size_t)m, cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    ex->last.epilogue_ms = ms;  // kernel-only time of the GEMM launch
+    ex->last.flops = (lower_only ? 1.0 : 2.0) * (double)m * (double)n * (double)k;
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ posterior
+namespace {
+struct StageEvents {
+    cudaEvent_t e[6];
+};
+}
+
+extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t N, const double* yres, int64_t yres_stride,
+                              const double* Xnew, int64_t P, int d, int64_t S, const double* theta, int noiseless, double jitter,
+                              unsigned flags, double* mean, double* var, double* cov, const double* eps, int64_t n_samp,
+                              double* y_sampled, int* info, b2gp_timing* timing) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xtr && yres && Xnew && theta && info);
+    ARG_CHECK(ctx, N >= 1 && P >= 1 && S >= 1 && d >= 1 && d <= GRAM_MAX_D);
+    ARG_CHECK(ctx, yres_stride == 0 || yres_stride >= N);
+    const bool want_mean = flags & B2GP_OUT_MEAN, want_var = flags & B2GP_OUT_VAR;
+    const bool want_cov = flags & B2GP_OUT_COV, want_samp = flags & B2GP_OUT_SAMPLE;
+    ARG_CHECK(ctx, !want_mean || mean);
+    ARG_CHECK(ctx, !want_var || var);
+    ARG_CHECK(ctx, !want_cov || cov);
+    ARG_CHECK(ctx, !want_samp || (eps && y_sampled && n_samp >= 1));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    const bool dev = dev_ptrs(flags);
+    const int nslots = (int)(S < ctx->n_streams ? S : ctx->n_streams);
+    cudaStream_t st0 = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st0));
+
+    // ---- inputs
+    const int nth = d + 3;
+    const double *dXtr, *dy, *dXnew, *dtheta, *deps = nullptr;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st0));
+    RET_IF(stage_in(ctx, st0, ctx->d_in[0], Xtr, (size_t)N * d * 8, dev, &dXtr));
+    RET_IF(stage_in(ctx, st0, ctx->d_in[1], yres, (size_t)(yres_stride ? S * yres_stride : N) * 8, dev, &dy));
+    RET_IF(stage_in(ctx, st0, ctx->d_in[2], Xnew, (size_t)P * d * 8, dev, &dXnew));
+    RET_IF(stage_in(ctx, st0, ctx->d_in[3], theta, (size_t)S * nth * 8, dev, &dtheta));
+    if (want_samp) RET_IF(stage_in(ctx, st0, ctx->d_in[4], eps, (size_t)S * n_samp * P * 8, dev, &deps));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st0));
+    CUDA_TRY(ctx, cudaEventRecord(ex->inputs_ready, st0));
+
+    // ---- outputs
+    double *dmean = mean, *dvar = var, *dcov = cov, *dsamp = y_sampled;
+    if (!dev) {
+        if (want_mean) {
+            RET_IF(ensure(ctx, ctx->d_out[0], (size_t)S * P * 8));
+            dmean = (double*)ctx->d_out[0].p;
+        }
+        if (want_var) {
+            RET_IF(ensure(ctx, ctx->d_out[1], (size_t)S * P * 8));
+            dvar = (double*)ctx->d_out[1].p;
+        }
+        if (want_cov) {
+            RET_IF(ensure(ctx, ctx->d_out[2], (size_t)S * P * P * 8));
+            dcov = (double*)ctx->d_out[2].p;
+        }
+        if (want_samp) {
+            RET_IF(ensure(ctx, ctx->d_out[3], (size_t)S * n_samp * P * 8));
+            dsamp = (double*)ctx->d_out[3].p;
+        }
+    }
+    RET_IF(ensure(ctx, ctx->d_info, (size_t)2 * S * sizeof(int)));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, (size_t)2 * S * sizeof(int), st0));
+
+    // ---- per-slot workspaces
+    const int64_t ldA = round_up(N, 8), ldV = ldA, ldC = round_up(P, 8);
+    const bool need_cov = want_cov || want_samp;
+    for (int q = 0; q < nslots; ++q) {
+        Slot& sl = ctx->slots[q];
+        RET_IF(ensure(ctx, sl.A, (size_t)N * ldA * 8));
+        RET_IF(ensure(ctx, sl.Vt, (size_t)(P + 1) * ldV * 8));
+        RET_IF(ensure(ctx, sl.Linv, (size_t)linv_bytes(N)));
+        if (need_cov) RET_IF(ensure(ctx, sl.cov, (size_t)P * ldC * 8));
+        if (want_samp) RET_IF(ensure(ctx, sl.LinvC, (size_t)linv_bytes(P)));
+        if (!want_mean) RET_IF(ensure(ctx, sl.misc, (size_t)P * 8));
+        if (q > 0) CUDA_TRY(ctx, cudaStreamWaitEvent(sl.stream, ex->inputs_ready, 0));
+    }
+    // the memset of dinfo was queued on st0 after inputs_ready: order the other streams behind it
+    if (nslots > 1) {
+        CUDA_TRY(ctx, cudaEventRecord(ex->inputs_ready, st0));
+        for (int q = 1; q < nslots; ++q) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->slots[q].stream, ex->inputs_ready, 0));
+    }
+
+    const double noise_mult_new = noiseless ? 0.0 : 1.0;  // gp.py:260-261
+    std::vector<StageEvents> sev;
+    if (timing) sev.resize((size_t)S);
+
+    for (int64_t s = 0; s < S; ++s) {
+        Slot& sl = ctx->slots[s % nslots];
+        cudaStream_t st = sl.stream;
+        double* A = (double*)sl.A.p;
+        double* Vt = (double*)sl.Vt.p;
+        double* Linv = (double*)sl.Linv.p;
+        const double* th = dtheta + s * nth;
+        int* inf = dinfo + s;
+        int* inf2 = dinfo + S + s;
+        if (timing) {
+            for (int e = 0; e < 6; ++e) sev[s].e[e] = ex->pool.get();
+            CUDA_TRY(ctx, cudaEventRecord(sev[s].e[0], st));
+        }
+        // k_XX = kernel(X_train, X_train, params, noise, jitter)  (gp.py:269) -- lower triangle only
+        RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXtr, N, d, th, 1.0, jitter, 1, 1, A, ldA));
+        if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
+        // factor instead of jnp.linalg.inv (gp.py:271)
+        RET_IF(potrf_rec(ctx, st, A, ldA, N, Linv, inf, 0));
+        if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[2], st));
+        // k_pX = kernel(X_new, X_train, params, jitter=0.0)  (gp.py:268); same-shape inputs add 0 there
+        RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXtr, N, d, th, 0.0, 0.0, 0, 0, Vt, ldV));
+        CUDA_TRY(ctx, cudaMemcpyAsync(Vt + P * ldV, dy + (yres_stride ? s * yres_stride : 0), (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+        if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[3], st));
+        // [V^T; w^T] = [k_pX; y^T] L^{-T}
+        RET_IF(trsm_rec(ctx, st, Vt, ldV, P + 1, A, ldA, N, Linv));
+        if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[4], st));
+        // mean / var
+        double* mean_s = want_mean ? dmean + s * P : (double*)sl.misc.p;
+        if (want_mean || want_var || want_samp) {
+            rowdot_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(Vt, ldV, N, P, kind, d, th, noise_mult_new, jitter, inf, mean_s,
+                                                           want_var ? dvar + s * P : nullptr);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+        if (need_cov) {
+            // cov = k_pp - V^T V  (gp.py:267, 272), lower tiles then mirrored -> exactly symmetric
+            double* C = want_cov ? dcov + s * P * P : (double*)sl.cov.p;
+            const int64_t ldc = want_cov ? P : ldC;
+            RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXnew, P, d, th, noise_mult_new, jitter, 1, 1, C, ldc));
+            RET_IF(gemm_nt(ctx, st, P, P, N, -1.0, Vt, ldV, Vt, ldV, 1.0, C, ldc, true));
+            dim3 g2((unsigned)ceil_div(P, 32), (unsigned)ceil_div(P, 32)), b2(32, 32);
+            mirror_lower_kernel<<<g2, b2, 0, st>>>(C, ldc, P);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+            if (want_samp) {
+                // y = mean + chol(cov) eps  (gp.py:292)
+                double* CL = (double*)sl.cov.p;
+                if (want_cov) {
+                    copy2d_kernel<<<grid_for(P * P), 256, 0, st>>>(CL, ldC, C, ldc, P, P);
+                    CUDA_TRY(ctx, cudaGetLastError());
+                    ctx->launches++;
+                }
+                RET_IF(potrf_rec(ctx, st, CL, ldC, P, (double*)sl.LinvC.p, inf2, 0));
+                zero_upper_kernel<<<g2, b2, 0, st>>>(CL, ldC, P);
+                double* Y = dsamp + s * n_samp * P;
+                bcast_rows_kernel<<<grid_for(n_samp * P), 256, 0, st>>>(Y, P, n_samp, P, mean_s);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches += 2;
+                RET_IF(gemm_nt(ctx, st, n_samp, P, P, 1.0, deps + s * n_samp * P, P, CL, ldC, 1.0, Y, P, false));
+                nan_if_bad_kernel<<<grid_for(n_samp * P), 256, 0, st>>>(Y, P, n_samp, P, inf, inf2);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches++;
+            }
+            if (want_cov) {
+                nan_if_bad_kernel<<<grid_for(P * P), 256, 0, st>>>(C, ldc, P, P, inf, nullptr);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches++;
+            }
+        }
+        if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[5], st));
+    }
+    // ---- join the slots on stream 0
+    for (int q = 1; q < nslots; ++q) {
+        CUDA_TRY(ctx, cudaEventRecord(ex->slot_done[q], ctx->slots[q].stream));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st0, ex->slot_done[q], 0));
+    }
+    cudaEvent_t ev_c = ctx->slots[0].ev[0], ev_d = ctx->slots[0].ev[1];
+    CUDA_TRY(ctx, cudaEventRecord(ev_c, st0));
+    std::vector<int> hinfo((size_t)2 * S);
+    CUDA_TRY(ctx, cudaMemcpyAsync(hinfo.data(), dinfo, (size_t)2 * S * sizeof(int), cudaMemcpyDeviceToHost, st0));
+    if (!dev) {
+        if (want_mean) CUDA_TRY(ctx, cudaMemcpyAsync(mean, dmean, (size_t)S * P * 8, cudaMemcpyDeviceToHost, st0));
+        if (want_var) CUDA_TRY(ctx, cudaMemcpyAsync(var, dvar, (size_t)S * P * 8, cudaMemcpyDeviceToHost, st0));
+        if (want_cov) CUDA_TRY(ctx, cudaMemcpyAsync(cov, dcov, (size_t)S * P * P * 8, cudaMemcpyDeviceToHost, st0));
+        if (want_samp) CUDA_TRY(ctx, cudaMemcpyAsync(y_sampled, dsamp, (size_t)S * n_samp * P * 8, cudaMemcpyDeviceToHost, st0));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ev_d, st0));
+    RET_IF(tm.end(st0, nullptr));
+    for (int64_t s = 0; s < S; ++s) info[s] = hinfo[s] != 0 ? hinfo[s] : -hinfo[S + s];
+
+    b2gp_timing& t = ex->last;
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    t.h2d_ms = ms;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ev_c, ev_d));
+    t.d2h_ms = ms;
+    if (timing) {
+        for (int64_t s = 0; s < S; ++s) {
+            float a = 0, b = 0, c = 0, e = 0, f = 0;
+            cudaEventElapsedTime(&a, sev[s].e[0], sev[s].e[1]);
+            cudaEventElapsedTime(&b, sev[s].e[1], sev[s].e[2]);
+            cudaEventElapsedTime(&c, sev[s].e[2], sev[s].e[3]);
+            cudaEventElapsedTime(&e, sev[s].e[3], sev[s].e[4]);
+            cudaEventElapsedTime(&f, sev[s].e[4], sev[s].e[5]);
+            t.gram_ms += a + c;
+            t.potrf_ms += b;
+            t.trsm_ms += e;
+            t.epilogue_ms += f;
+        }
+    }
+    const double n = (double)N, p = (double)P;
+    t.flops = (double)S * (n * n * n / 3.0 + n * n * (p + 1.0) + 4.0 * n * p + (need_cov ? n * p * p : 0.0));
+    t.gram_bytes = (double)S * (8.0 * n * n / 2.0 + 8.0 * n * p + (need_cov ? 8.0 * p * p : 0.0));
+    if (timing) *timing = t;
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ sparse posterior
+// out[r, c] = in[c, r]
+__global__ void transpose_kernel(double* __restrict__ out, int64_t ldo, const double* __restrict__ in, int64_t ldi,
+                                 int64_t rows_in, int64_t cols_in) {
+    __shared__ double tile[32][33];
+    const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows_in && c < cols_in) ? in[r * ldi + c] : 0.0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int64_t r = c0 + i, c = r0 + threadIdx.x;  // out coordinates
+        if (r < cols_in && c < rows_in) out[r * ldo + c] = tile[threadIdx.x][i];
+    }
+}
+
+// generic <row, w> and |row|^2 reductions: dot[p] = <R[p,:], w>, nrm[p] = |R[p,:]|^2
+__global__ void __launch_bounds__(RD_THREADS)
+rowdot2_kernel(const double* __restrict__ R, int64_t ld, int64_t len, const double* __restrict__ w, double wscale,
+               double* __restrict__ dot, double* __restrict__ nrm) {
+    __shared__ double red1[RD_THREADS / 32], red2[RD_THREADS / 32];
+    const double* row = R + (int64_t)blockIdx.x * ld;
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t k = threadIdx.x; k < len; k += RD_THREADS) {
+        const double v = row[k];
+        if (w) s1 = fma(v, w[k], s1);
+        s2 = fma(v, v, s2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red1[threadIdx.x >> 5] = s1;
+        red2[threadIdx.x >> 5] = s2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < RD_THREADS / 32; ++i) {
+            a += red1[i];
+            b += red2[i];
+        }
+        if (dot) dot[blockIdx.x] = a * wscale;
+        if (nrm) nrm[blockIdx.x] = b;
+    }
+}
+
+// var[p] = kdiag - q[p] + r[p];  NaN when the factorisations failed
+__global__ void sparse_var_kernel(double* var, double* mean, const double* q, const double* r, int64_t P, int kind, int d,
+                                  const double* theta, double noise_mult, double jitter, const int* info, const int* info2) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const bool bad = (*info != 0) || (*info2 != 0);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (var) {
+        const double kd = cov_self(kind, theta[d]) + (theta[d + 1] * noise_mult + jitter);
+        var[p] = bad ? nan : (kd - q[p]) + r[p];
+    }
+    if (mean && bad) mean[p] = nan;
+}
+
+__global__ void scale_by_inv_noise_kernel(double* v, int64_t n, const double* theta, int d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = v[i] / theta[d + 1];
+}
+
+extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* Xtr, int64_t N,
+                                     const double* yres, const double* Xnew, int64_t P, int d, const double* theta, int noiseless,
+                                     double jitter, unsigned flags, double* mean, double* var, double* cov, int* info,
+                                     b2gp_timing* timing) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xu && Xtr && yres && Xnew && theta && info);
+    ARG_CHECK(ctx, M >= 1 && N >= 1 && P >= 1 && d >= 1 && d <= GRAM_MAX_D);
+    const bool want_mean = flags & B2GP_OUT_MEAN, want_var = flags & B2GP_OUT_VAR, want_cov = flags & B2GP_OUT_COV;
+    ARG_CHECK(ctx, !want_mean || mean);
+    ARG_CHECK(ctx, !want_var || var);
+    ARG_CHECK(ctx, !want_cov || cov);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    const bool dev = dev_ptrs(flags);
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const int nth = d + 3;
+    const double *dXu, *dXtr, *dy, *dXnew, *dth;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], Xtr, (size_t)N * d * 8, dev, &dXtr));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], yres, (size_t)N * 8, dev, &dy));
+    RET_IF(stage_in(ctx, st, ctx->d_in[2], Xnew, (size_t)P * d * 8, dev, &dXnew));
+    RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, dev, &dth));
+    RET_IF(stage_in(ctx, st, ctx->d_in[5], Xu, (size_t)M * d * 8, dev, &dXu));
+
+    const int64_t ldM = round_up(M, 8), ldN = round_up(N, 8), ldC = round_up(P, 8);
+    // workspaces (slot 0): A <- Kuu/Luu (M x ldM) and Kmat/L (M x ldM); Vt <- Wt (N x ldM); cov buffer <- W (M x ldN)
+    RET_IF(ensure(ctx, sl.A, (size_t)2 * M * ldM * 8));
+    RET_IF(ensure(ctx, sl.Vt, (size_t)N * ldM * 8));
+    RET_IF(ensure(ctx, sl.cov, (size_t)M * ldN * 8));
+    RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
+    RET_IF(ensure(ctx, sl.LinvC, (size_t)2 * (P + 1) * ldM * 8 + (size_t)P * ldC * 8));
+    RET_IF(ensure(ctx, sl.misc, (size_t)(4 * P + 2 * M + 16) * 8));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
+    double* Luu = (double*)sl.A.p;
+    double* Kmat = Luu + M * ldM;
+    double* Wt = (double*)sl.Vt.p;
+    double* W = (double*)sl.cov.p;
+    double* LinvU = (double*)sl.Linv.p;
+    double* LinvK = LinvU + linv_bytes(M) / 8;
+    double* Wst = (double*)sl.LinvC.p;          // (P) x ldM        Ws^T = K_su Luu^{-T}
+    double* R = Wst + (P + 1) * ldM;            // (P+1) x ldM      rows 0..P-1: Ws^T then (L^{-1} Ws)^T; row P: c then L^{-1} c
+    double* Cb = R + (P + 1) * ldM;             // P x ldC          covariance staging (host mode)
+    double* qv = (double*)sl.misc.p;            // |Ws^T[p]|^2
+    double* rv = qv + P;                        // |R[p]|^2
+    double* mv = rv + P;                        // mean staging
+    double* vv = mv + P;                        // var staging
+    double* cvec = vv + P;                      // W D^-1 y (M)
+
+    // Kuu = kernel(Xu, Xu, params, **kwargs): noise defaults to 0, so the diagonal gets jitter only (sparse_gp.py:193)
+    RET_IF(launch_gram(ctx, st, kind, dXu, M, dXu, M, d, dth, 0.0, jitter, 1, 1, Luu, ldM));
+    RET_IF(potrf_rec(ctx, st, Luu, ldM, M, LinvU, dinfo, 0));                                   // sparse_gp.py:194
+    // W^T = K_fu Luu^{-T}  (W = Luu^{-1} Kuf, sparse_gp.py:195-197), one training point per row
+    RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wt, ldM));
+    RET_IF(trsm_rec(ctx, st, Wt, ldM, N, Luu, ldM, M, LinvU));
+    {
+        dim3 g((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32)), b(32, 8);
+        transpose_kernel<<<g, b, 0, st>>>(W, ldN, Wt, ldM, N, M);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    // K = W D^{-1} W^T + I with D = noise * 1  (sparse_gp.py:198-200); 1/noise applied after the sum
+    {
+        double noise_h = 0.0;
+        if (dev)
+            CUDA_TRY(ctx, cudaMemcpyAsync(&noise_h, dth + d + 1, 8, cudaMemcpyDeviceToHost, st));
+        else
+            noise_h = theta[d + 1];
+        if (dev) CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        RET_IF(gemm_nt(ctx, st, M, M, N, 1.0 / noise_h, W, ldN, W, ldN, 0.0, Kmat, ldM, true));
+    }
+    add_diag_kernel<<<grid_for(M), 256, 0, st>>>(Kmat, ldM, M, 1.0);
+    CUDA_TRY(ctx, cudaGetLastError());
+    RET_IF(potrf_rec(ctx, st, Kmat, ldM, M, LinvK, dinfo + 1, 0));                              // sparse_gp.py:201
+    // c = W D^{-1} y  (sparse_gp.py:203-204)
+    rowdot2_kernel<<<(unsigned)M, RD_THREADS, 0, st>>>(W, ldN, N, dy, 1.0, cvec, nullptr);
+    scale_by_inv_noise_kernel<<<grid_for(M), 256, 0, st>>>(cvec, M, dth, d);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    // Ws^T = K_su Luu^{-T}  (sparse_gp.py:206-207)
+    RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wst, ldM));
+    RET_IF(trsm_rec(ctx, st, Wst, ldM, P, Luu, ldM, M, LinvU));
+    // pack = [c | Ws]; L^{-1} pack  (sparse_gp.py:208-212)
+    copy2d_kernel<<<grid_for(P * M), 256, 0, st>>>(R, ldM, Wst, ldM, P, M);
+    CUDA_TRY(ctx, cudaMemcpyAsync(R + P * ldM, cvec, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+    ctx->launches++;
+    RET_IF(trsm_rec(ctx, st, R, ldM, P + 1, Kmat, ldM, M, LinvK));
+    // mean = (L^{-1} c)^T (L^{-1} Ws)  (sparse_gp.py:213)
+    double* dmean = want_mean ? (dev ? mean : mv) : mv;
+    double* dvar = want_var ? (dev ? var : vv) : nullptr;
+    rowdot2_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(R, ldM, M, R + P * ldM, 1.0, dmean, rv);
+    rowdot2_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(Wst, ldM, M, nullptr, 1.0, nullptr, qv);
+    sparse_var_kernel<<<grid_for(P), 256, 0, st>>>(dvar, dmean, qv, rv, P, kind, d, dth, noiseless ? 0.0 : 1.0, jitter, dinfo, dinfo + 1);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    if (want_cov) {
+        // cov = Kss - Ws^T Ws + (L^{-1}Ws)^T (L^{-1}Ws)  (sparse_gp.py:215-217)
+        double* C = dev ? cov : Cb;
+        const int64_t ldc = dev ? P : ldC;
+        RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXnew, P, d, dth, noiseless ? 0.0 : 1.0, jitter, 1, 1, C, ldc));
+        RET_IF(gemm_nt(ctx, st, P, P, M, -1.0, Wst, ldM, Wst, ldM, 1.0, C, ldc, true));
+        RET_IF(gemm_nt(ctx, st, P, P, M, 1.0, R, ldM, R, ldM, 1.0, C, ldc, true));
+        dim3 g2((unsigned)ceil_div(P, 32), (unsigned)ceil_div(P, 32)), b2(32, 32);
+        mirror_lower_kernel<<<g2, b2, 0, st>>>(C, ldc, P);
+        nan_if_bad_kernel<<<grid_for(P * P), 256, 0, st>>>(C, ldc, P, P, dinfo, dinfo + 1);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 2;
+        if (!dev) CUDA_TRY(ctx, cudaMemcpy2DAsync(cov, (size_t)P * 8, C, (size_t)ldc * 8, (size_t)P * 8, (size_t)P, cudaMemcpyDeviceToHost, st));
+    }
+    int hinfo[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!dev) {
+        if (want_mean) CUDA_TRY(ctx, cudaMemcpyAsync(mean, dmean, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+        if (want_var) CUDA_TRY(ctx, cudaMemcpyAsync(var, dvar, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    }
+    RET_IF(tm.end(st, nullptr));
+    info[0] = hinfo[0] != 0 ? hinfo[0] : -hinfo[1];
+    const double m = (double)M, n = (double)N, p = (double)P;
+    ex->last.flops = 2.0 * m * m * m / 3.0 + 2.0 * m * m * n + 2.0 * m * m * (p + 1.0) + (want_cov ? 2.0 * m * p * p : 0.0);
+    ex->last.gram_bytes = 8.0 * (m * n + m * m / 2.0 + m * p);
+    if (timing) *timing = ex->last;
+    return B2GP_OK;
+}

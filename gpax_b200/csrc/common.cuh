@@ -1,0 +1,96 @@
+// common.cuh -- context, error handling, device buffers for libb200gp.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200gp.h"
+
+#define B2GP_MAX_STREAMS 4
+#define B2GP_LEAF 128  // diagonal-block size of the factorisation (one CTA, shared memory)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+// One "slot" = the workspace of one posterior draw in flight.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    DevBuf A;      // N x ldA      k_XX, then its factor L (lower)
+    DevBuf Vt;     // (P+1) x ldV  rows 0..P-1 = k_pX (gp.py:268), row P = y_res; then V^T, w^T
+    DevBuf Linv;   // nblk x 128 x 128 inverted diagonal blocks of L
+    DevBuf cov;    // P x ldC      posterior covariance / its factor
+    DevBuf LinvC;  // inverted diagonal blocks of chol(cov)
+    DevBuf misc;   // small scratch
+    cudaEvent_t ev[8];
+};
+
+struct b2gp_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    size_t mem_bytes = 0;
+    int n_streams = 2;
+    Slot slots[B2GP_MAX_STREAMS];
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
+    // staging for host-pointer entry points
+    DevBuf d_in[8];
+    DevBuf d_out[4];
+    DevBuf d_info;
+    // factor bookkeeping for b2gp_trsm_lower (host-pointer mode keeps the factor resident)
+    DevBuf last_linv;
+    int64_t last_n = 0;
+    int64_t launches = 0;
+    std::string err;
+};
+
+static inline int set_err(b2gp_ctx* ctx, int code, const char* what, const char* detail, const char* file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, detail ? detail : "", file, line);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return set_err((ctx), B2GP_ERR_CUDA, #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define ARG_CHECK(ctx, cond)                                                                       \
+    do {                                                                                           \
+        if (!(cond)) return set_err((ctx), B2GP_ERR_ARG, "bad argument", #cond, __FILE__, __LINE__); \
+    } while (0)
+
+#define RET_IF(expr)                \
+    do {                            \
+        int r_ = (expr);            \
+        if (r_ != B2GP_OK) return r_; \
+    } while (0)
+
+static inline int ensure(b2gp_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.cap >= bytes && b.p) return B2GP_OK;
+    if (b.p) {
+        CUDA_TRY(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    // round up so that slowly growing requests do not re-allocate every call
+    size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return set_err(ctx, B2GP_ERR_NOMEM, "cudaMalloc", cudaGetErrorString(e), __FILE__, __LINE__);
+    }
+    b.cap = want;
+    return B2GP_OK;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }

@@ -1,0 +1,164 @@
+/*
+ * b200gp.h -- C-ABI of libb200gp.so: the B200-native exact-GP posterior path.
+ *
+ * The reference (ziatdinovmax/gpax v0.1.9) is pure Python on JAX and has no FFI; its two seams on
+ * this path are Python callables:
+ *   kernel seam     gpax/kernels/kernels.py:17      kernel(X, Z, params, noise, jitter) -> K
+ *   posterior seam  gpax/models/gp.py:253-255       get_mvn_posterior(X_new, params, noiseless, **kw)
+ * The entry points below are what a ctypes binding placed behind those two callables calls
+ * (INTEGRATION.md shows the stub).  Every entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - plain C symbols, plain pointers and sizes; no torch / numpy types
+ *   - all matrices are fp64, ROW-MAJOR with an explicit leading dimension (elements)
+ *   - pointers are HOST pointers unless B2GP_FLAG_DEVICE_PTRS is set in `flags`, in which case every
+ *     array argument (not `info`, not `timing`) is a device pointer obtained from b2gp_dev_alloc
+ *   - the caller owns every buffer it passes; the library owns only the ctx and its workspaces
+ *   - return value: 0 ok, <0 argument / CUDA failure (text via b2gp_last_error).  A numerical failure
+ *     is NOT an error status: `info[s] > 0` is the 1-based index of the first non-positive pivot of
+ *     draw s and that draw's outputs are NaN (the reference yields NaNs, never an exception, and
+ *     post-filters them: gpax/models/gp.py:396-398)
+ *   - a ctx is not thread-safe; calls are synchronous from the caller's point of view
+ */
+#ifndef B200GP_H
+#define B200GP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2GP_VERSION 100
+
+typedef struct b2gp_ctx b2gp_ctx;
+
+/* kernel families: gpax/kernels/kernels.py:44-65 (RBF), 68-91 (Matern-5/2), 94-117 (Periodic);
+ * name table gpax/kernels/kernels.py:227-241 */
+enum { B2GP_KERNEL_RBF = 0, B2GP_KERNEL_MATERN52 = 1, B2GP_KERNEL_PERIODIC = 2 };
+
+enum {
+    B2GP_OK = 0,
+    B2GP_ERR_ARG = -1,
+    B2GP_ERR_CUDA = -2,
+    B2GP_ERR_NOMEM = -3,
+    B2GP_ERR_UNSUPPORTED = -4
+};
+
+enum {
+    B2GP_FLAG_DEVICE_PTRS = 1u << 0, /* array arguments are device pointers                                  */
+    B2GP_FLAG_LOWER_ONLY  = 1u << 1, /* b2gp_gram with same_xz: write only the lower triangle (j <= i)       */
+    B2GP_OUT_MEAN         = 1u << 4, /* b2gp_posterior: produce mean[S,P]                                    */
+    B2GP_OUT_VAR          = 1u << 5, /* ... var[S,P] = diag(cov)     (viGP.predict, vigp.py:184-185)         */
+    B2GP_OUT_COV          = 1u << 6, /* ... cov[S,P,P]               (get_mvn_posterior, gp.py:272)          */
+    B2GP_OUT_SAMPLE       = 1u << 7  /* ... y_sampled[S,n,P] = mean + chol(cov) eps   (gp.py:292)            */
+};
+
+/* per-call device timing (CUDA events on the library's own streams), filled when non-NULL.
+ * The *_ms stage fields are sums of stream time over the draws (they can exceed total_ms when
+ * several draws are in flight); total_ms is first-launch to last-completion on the device,
+ * h2d/d2h are the host<->device copies of the host-pointer entry points. */
+typedef struct b2gp_timing {
+    double total_ms;
+    double gram_ms;
+    double potrf_ms;
+    double trsm_ms;
+    double epilogue_ms;
+    double h2d_ms;
+    double d2h_ms;
+    double flops;        /* algorithmic flops of the call: S * (N^3/3 + N^2 (P+1) + ...)   */
+    double gram_bytes;   /* algorithmic bytes written by the Gram builds                                 */
+    int64_t launches;    /* kernels launched by the call                                                 */
+} b2gp_timing;
+
+int  b2gp_version(void);
+
+/* lifecycle --------------------------------------------------------------------------------------*/
+int  b2gp_ctx_create(int device, b2gp_ctx** out);
+int  b2gp_ctx_destroy(b2gp_ctx* ctx);
+const char* b2gp_last_error(const b2gp_ctx* ctx);
+/* options: "streams" (draws in flight, 1..4, default 2), "leaf" ignored for now */
+int  b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value);
+int  b2gp_device_info(b2gp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* mem_bytes);
+/* device timing of the most recent entry-point call on this ctx (every call records total_ms) */
+int  b2gp_last_timing(b2gp_ctx* ctx, b2gp_timing* out);
+
+/* device memory, for callers that keep inputs resident in HBM (replaces jax.device_put,
+ * gpax/models/gp.py:388-391,416-428) ----------------------------------------------------------------*/
+int  b2gp_dev_alloc(b2gp_ctx* ctx, size_t bytes, void** dptr);
+int  b2gp_dev_free(b2gp_ctx* ctx, void* dptr);
+int  b2gp_host_alloc(b2gp_ctx* ctx, size_t bytes, void** hptr);   /* pinned host memory */
+int  b2gp_host_free(b2gp_ctx* ctx, void* hptr);
+int  b2gp_h2d(b2gp_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+int  b2gp_d2h(b2gp_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+int  b2gp_sync(b2gp_ctx* ctx);
+
+/* Gram build -- replaces square_scaled_distance + RBFKernel / MaternKernel / PeriodicKernel
+ * (gpax/kernels/kernels.py:28-41, 44-65, 68-91, 94-117).
+ *   X[n,d], Z[m,d] row-major; lengthscale[d] (a scalar lengthscale is broadcast by the caller);
+ *   K[n,m] with leading dimension ldk.  `diag_add` = noise + jitter is added on i == j iff
+ *   same_xz != 0; the caller sets same_xz from the reference's rule `X.shape == Z.shape`
+ *   (kernels.py:63, 89, 115).  `period` is read for B2GP_KERNEL_PERIODIC only.                     */
+int  b2gp_gram(b2gp_ctx* ctx, int kind,
+               const double* X, int64_t n, const double* Z, int64_t m, int d,
+               const double* lengthscale, double scale, double period,
+               double diag_add, int same_xz,
+               double* K, int64_t ldk, unsigned flags);
+
+/* Cholesky factorisation A = L L^T of the lower triangle, in place (row-major, lower); the strict
+ * upper triangle is not referenced and not modified.  Stands where the reference inverts k_XX
+ * (jnp.linalg.inv, gpax/models/gp.py:271) and where viSparseGP calls jax.scipy.linalg.cholesky
+ * (gpax/models/sparse_gp.py:194,201).  *info = 0, or the 1-based index of the first bad pivot.      */
+int  b2gp_potrf(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, int* info, unsigned flags);
+
+/* Triangular solve with the factor: overwrites the nrhs right-hand sides with L^{-1} b.
+ * B holds one right-hand side per ROW: B[r, 0..n) is b_r, leading dimension ldb (i.e. the n x nrhs
+ * matrix of right-hand sides in column-major order).  Replaces solve_triangular(L, ., lower=True)
+ * (gpax/models/sparse_gp.py:197,207,209) and the K^{-1} products of gp.py:272-273.
+ * L must be the output of b2gp_potrf made through the same ctx immediately before (the solve
+ * reuses the inverted diagonal blocks that factorisation left in the ctx).                          */
+int  b2gp_trsm_lower(b2gp_ctx* ctx, int64_t n, int64_t nrhs,
+                     const double* L, int64_t ldl, double* B, int64_t ldb, unsigned flags);
+
+/* C[m,n] = beta C + alpha A[m,k] B[n,k]^T (fp64, DMMA tensor pipe); lower_only != 0 updates only
+ * j <= i (SYRK when A == B).  The trailing-update kernel of the factorisation, exported for the
+ * roofline measurement and the parity tests; replaces the jnp.matmul calls of gp.py:272-273.       */
+int  b2gp_gemm_nt(b2gp_ctx* ctx, int64_t m, int64_t n, int64_t k, double alpha,
+                  const double* A, int64_t lda, const double* B, int64_t ldb,
+                  double beta, double* C, int64_t ldc, int lower_only, unsigned flags);
+
+/* The posterior, batched over S hyper-parameter draws -- replaces ExactGP.get_mvn_posterior
+ * (gpax/models/gp.py:253-277), _predict's sampling (gp.py:279-293), the vmap over draws in predict
+ * (gp.py:393-395) and viGP.predict (gpax/models/vigp.py:178-185).
+ *   Xtr[N,d], Xnew[P,d]                    row-major
+ *   yres[N] (yres_stride == 0) or yres[S, yres_stride]   y_train minus the mean function (gp.py:262-265)
+ *   theta[S, d+3]                          per draw: lengthscale[0..d), k_scale, noise, period
+ *   noiseless                              gp.py:260-261: noise_p = noise * (1 - noiseless)
+ *   jitter                                 the **kwargs jitter of gp.py:267,269 (default 1e-6)
+ *   flags                                  B2GP_OUT_* (+ B2GP_FLAG_DEVICE_PTRS)
+ *   mean[S,P], var[S,P], cov[S,P,P]        outputs selected by flags (others may be NULL)
+ *   eps[S,n_samp,P], y_sampled[S,n_samp,P] standard-normal draws in, posterior samples out
+ *   info[S]                                0 or first bad pivot of k_XX (>0) / of cov (<0, sampling)  */
+int  b2gp_posterior(b2gp_ctx* ctx, int kind,
+                    const double* Xtr, int64_t N, const double* yres, int64_t yres_stride,
+                    const double* Xnew, int64_t P, int d, int64_t S,
+                    const double* theta, int noiseless, double jitter, unsigned flags,
+                    double* mean, double* var, double* cov,
+                    const double* eps, int64_t n_samp, double* y_sampled,
+                    int* info, b2gp_timing* timing);
+
+/* Nystrom / VFE sparse posterior for one theta -- replaces viSparseGP.get_mvn_posterior
+ * (gpax/models/sparse_gp.py:173-223).  Xu[M,d] inducing points; theta[d+3] as above;
+ * outputs mean[P] and var[P] (B2GP_OUT_VAR) and/or cov[P,P] (B2GP_OUT_COV).                        */
+int  b2gp_sparse_posterior(b2gp_ctx* ctx, int kind,
+                           const double* Xu, int64_t M, const double* Xtr, int64_t N, const double* yres,
+                           const double* Xnew, int64_t P, int d,
+                           const double* theta, int noiseless, double jitter, unsigned flags,
+                           double* mean, double* var, double* cov,
+                           int* info, b2gp_timing* timing);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GP_H */
