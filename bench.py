@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""
+bench.py -- GP posteriors/s at N=16384 (BASELINE.json metric) on N GPUs of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU; ranks process independent posterior draws -- the
+   path's natural sharding, SURVEY.md section 8e "draw-parallel" -- so scaling is weak and there is no
+   data-path collective; torch.distributed is used only for the barrier and the max-over-ranks.)
+
+A "step" is one pass of the hot path over one batch of S hyper-parameter draws: for each draw
+Gram(k_XX) -> N x N Cholesky -> Gram(k_pX) -> triangular solves -> posterior mean + diagonal variance
+(the replacement of gpax/models/gp.py:253-277 under the vmap of gp.py:393-395).
+
+  value   posteriors/s with X, y, X_new, theta resident in HBM (device-pointer C-ABI call)
+  e2e     the same through the host-buffer C-ABI call (pinned host memory in, host memory out:
+          H2D of X, y, X_new, theta and D2H of mean, var, info inside the timed region)
+  roofline  dominant kernel = the DMMA trailing-update GEMM/SYRK (gemm_nt_kernel): algorithmic flops of
+          the top-level SYRK of the N=16384 factorisation (8192 x 8192, k = 8192, lower half) / its
+          CUDA-event duration, against the fp64 GEMM peak measured live with cuBLAS (torch.matmul fp64;
+          MEASURED_PEAKS.json carries no fp64 figure)
+  cpu_baseline  the oracle's restatement of the reference formulation (explicit inverse,
+          oracle.exact_posterior) timed on the host cores on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="exactgp_rbf_N16384_d3_P1024", N=16384, d=3, P=1024, kernel="RBF", ell=0.3, scale=1.0, noise=0.1,
+                jitter=1e-6, S=8)
+
+
+def make_inputs(rank):
+    """SURVEY.md section 8d 'headline' row: N=16384, d=3, U(0,1)^3, seed 4 (+rank), RBF l=0.3, noise 0.1, P=1024."""
+    w = WORKLOAD
+    rng = np.random.default_rng(4 + 1000 * rank)
+    X = rng.uniform(0, 1, (w["N"], w["d"]))
+    y = np.sin(3 * X[:, 0]) * np.cos(2 * X[:, 1]) + X[:, 2] + 0.1 * rng.standard_normal(w["N"])
+    Xn = rng.uniform(0, 1, (w["P"], w["d"]))
+    # S draws around the nominal hyper-parameters (every draw is a different K: nothing can be cached)
+    S = w["S"]
+    theta = np.empty((S, w["d"] + 3))
+    theta[:, :w["d"]] = w["ell"] * np.exp(0.05 * rng.standard_normal((S, w["d"])))
+    theta[:, w["d"]] = w["scale"] * np.exp(0.05 * rng.standard_normal(S))
+    theta[:, w["d"] + 1] = w["noise"] * np.exp(0.05 * rng.standard_normal(S))
+    theta[:, w["d"] + 2] = 1.0
+    return X, y, Xn, theta
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    td = None
+    if world > 1:
+        import torch
+        import torch.distributed as td_
+        torch.cuda.set_device(local)
+        td_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        td = td_
+    return rank, world, local, td
+
+
+def barrier_sync(td, local):
+    if td is not None:
+        import torch
+        td.barrier()
+        torch.cuda.synchronize(local)
+
+
+def max_over_ranks(td, local, value):
+    if td is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{local}")
+    td.all_reduce(t, op=td.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure_fp64_peak(local):
+    """cuBLAS DGEMM 8192^3 (torch.matmul fp64), best of 5 after warm-up, CUDA events: the fp64 denominator."""
+    import torch
+    dev = f"cuda:{local}"
+    a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2 * 8192 ** 3 / best / 1e9  # TFLOP/s
+
+
+def measure_dominant_kernel(ctx, ffi):
+    """The trailing-update SYRK at the headline size, device resident, CUDA events around the launch."""
+    n = 8192
+    rng = np.random.default_rng(0)
+    A = ctx.to_device(rng.standard_normal((n, n)))
+    Cm = ctx.to_device(np.zeros((n, n)))
+    ms = []
+    for _ in range(5):
+        ctx._check(ctx.lib.b2gp_gemm_nt(ctx.h, n, n, n, -1.0, A.ptr, n, A.ptr, n, 1.0, Cm.ptr, n, 1, ffi.FLAG_DEVICE_PTRS))
+        ms.append(ctx.last_timing()["epilogue_ms"])
+    A.free()
+    Cm.free()
+    ms = float(np.mean(ms[2:]))
+    return {"flops_per_launch": float(n) ** 3, "ms": ms, "tflops": float(n) ** 3 / ms / 1e9}
+
+
+def cpu_baseline(budget_s=30.0):
+    """The oracle (port of the reference formulation, np.linalg.inv) on the host cores, bounded sample."""
+    import oracle
+    w = WORKLOAD
+    cores = os.cpu_count()
+    rng = np.random.default_rng(4)
+    params = {"k_length": np.full(w["d"], w["ell"]), "k_scale": w["scale"], "noise": w["noise"]}
+
+    def run(N):
+        X = rng.uniform(0, 1, (N, w["d"]))
+        y = rng.standard_normal(N)
+        Xn = rng.uniform(0, 1, (w["P"], w["d"]))
+        t0 = time.perf_counter()
+        oracle.exact_posterior(X, y, Xn, params, "RBF", jitter=w["jitter"])
+        return time.perf_counter() - t0
+    run(1024)
+    t4 = run(4096)
+    est_full = t4 * (w["N"] / 4096) ** 3
+    if est_full <= budget_s * 1.5:
+        t = run(w["N"])
+        return {"value": 1.0 / t, "unit": "posteriors/s", "cores": cores, "kind": "port",
+                "sample": f"1 posterior at N={w['N']} P={w['P']} (oracle.exact_posterior, explicit inverse), {t:.1f} s"}
+    N = 4096
+    while N * 2 <= w["N"] and t4 * ((N * 2) / 4096) ** 3 <= budget_s:
+        N *= 2
+    t = run(N) if N != 4096 else t4
+    scaled = t * (w["N"] / N) ** 3
+    return {"value": 1.0 / scaled, "unit": "posteriors/s", "cores": cores, "kind": "port",
+            "sample": f"1 posterior at N={N} ({t:.1f} s) scaled by (16384/{N})^3 to N={w['N']} = {scaled:.1f} s"}
+
+
+def run_reference_arm(args, rank):
+    """--impl reference: the reference's own CPU formulation (gpax cannot be imported: JAX absent; the oracle is
+    its op-for-op NumPy restatement), all host threads, same config / metric / unit."""
+    if rank != 0:
+        return
+    w = WORKLOAD
+    import oracle
+    cores = os.cpu_count()
+    # each step is a bounded sample: one posterior at N_s, scaled to N=16384 by the N^3 flop law
+    params = {"k_length": np.full(w["d"], w["ell"]), "k_scale": w["scale"], "noise": w["noise"]}
+    rng = np.random.default_rng(4)
+    Ns = 4096
+    X = rng.uniform(0, 1, (Ns, w["d"]))
+    y = rng.standard_normal(Ns)
+    Xn = rng.uniform(0, 1, (w["P"], w["d"]))
+    t_probe0 = time.perf_counter()
+    oracle.exact_posterior(X, y, Xn, params, "RBF", jitter=w["jitter"])
+    t_probe = time.perf_counter() - t_probe0
+    total_steps = args.steps + args.warmup
+    while Ns * 2 <= w["N"] and t_probe * 8 * total_steps <= 150.0:
+        Ns *= 2
+        t_probe *= 8
+    X = rng.uniform(0, 1, (Ns, w["d"]))
+    y = rng.standard_normal(Ns)
+    for _ in range(args.warmup):
+        oracle.exact_posterior(X, y, Xn, params, "RBF", jitter=w["jitter"])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.exact_posterior(X, y, Xn, params, "RBF", jitter=w["jitter"])
+    t = (time.perf_counter() - t0) / args.steps
+    scaled = t * (w["N"] / Ns) ** 3
+    val = 1.0 / scaled
+    line = {"impl": "reference", "metric": "gp_posteriors_per_s_N16384", "value": val, "unit": "posteriors/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": scaled * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "N": w["N"], "d": w["d"], "P": w["P"], "kernel": w["kernel"]},
+            "cpu_baseline": {"value": val, "unit": "posteriors/s", "cores": cores, "kind": "port",
+                             "sample": f"one posterior per step at N={Ns} ({t:.2f} s) scaled by ({w['N']}/{Ns})^3; "
+                                       "oracle.exact_posterior = NumPy restatement of gpax ExactGP.get_mvn_posterior "
+                                       "(explicit inverse); gpax itself needs JAX, which is not installable here"},
+            "e2e": {"value": val, "unit": "posteriors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        run_reference_arm(args, int(os.environ.get("RANK", "0")))
+        return
+
+    rank, world, local, td = dist_setup(args.gpus)
+    from gpax_b200 import _ffi as ffi
+    w = WORKLOAD
+    ctx = ffi.Context(local)
+    ctx.set_option("streams", args.streams)
+    X, y, Xn, theta = make_inputs(rank)
+    N, d, P, S = w["N"], w["d"], w["P"], w["S"]
+    flags_out = ffi.OUT_MEAN | ffi.OUT_VAR
+
+    # ---- device-resident arm ("value")
+    dX, dy, dXn, dth = ctx.to_device(X), ctx.to_device(y), ctx.to_device(Xn), ctx.to_device(theta)
+    dmean, dvar = ctx.alloc((S, P)), ctx.alloc((S, P))
+    info = np.zeros(S, dtype=np.int32)
+    tim = ffi.Timing()
+
+    def step_device():
+        ctx._check(ctx.lib.b2gp_posterior(ctx.h, ffi.KIND[w["kernel"]], dX.ptr, N, dy.ptr, 0, dXn.ptr, P, d, S, dth.ptr, 0,
+                                          w["jitter"], flags_out | ffi.FLAG_DEVICE_PTRS, dmean.ptr, dvar.ptr, None, None, 0,
+                                          None, info.ctypes.data, None))
+        t = ctx.last_timing()
+        return t["total_ms"], t["launches"]
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    assert (info == 0).all(), f"factorisation failed in warm-up: info={info}"
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier_sync(td, local)
+    ctx.sync()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        ms, nl = step_device()
+        dev_ms += ms
+        launches += nl
+    ctx.sync()
+    barrier_sync(td, local)
+    t1 = time.perf_counter()
+    clocks = sampler.stop(t0, t1)
+    wall_ms = (t1 - t0) * 1e3
+    dev_ms = max_over_ranks(td, local, dev_ms)
+    wall_ms = max_over_ranks(td, local, wall_ms)
+    value = world * S * args.steps / (dev_ms / 1e3)
+
+    # ---- end-to-end arm: host (pinned) buffers through the C-ABI
+    hX, hy, hXn, hth = ctx.pinned((N, d)), ctx.pinned((N,)), ctx.pinned((P, d)), ctx.pinned((S, d + 3))
+    hX[:], hy[:], hXn[:], hth[:] = X, y, Xn, theta
+    hmean, hvar = ctx.pinned((S, P)), ctx.pinned((S, P))
+
+    def step_host():
+        ctx._check(ctx.lib.b2gp_posterior(ctx.h, ffi.KIND[w["kernel"]], hX.ctypes.data, N, hy.ctypes.data, 0, hXn.ctypes.data,
+                                          P, d, S, hth.ctypes.data, 0, w["jitter"], flags_out, hmean.ctypes.data,
+                                          hvar.ctypes.data, None, None, 0, None, info.ctypes.data, None))
+    step_host()
+    barrier_sync(td, local)
+    ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    ctx.sync()
+    barrier_sync(td, local)
+    e2e_s = max_over_ranks(td, local, time.perf_counter() - t0)
+    e2e_value = world * S * args.steps / e2e_s
+    assert np.isfinite(hmean).all() and (hvar > 0).all()
+    h2d = X.nbytes + y.nbytes + Xn.nbytes + theta.nbytes
+    d2h = hmean.nbytes + hvar.nbytes + info.nbytes
+
+    if rank != 0:
+        if td is not None:
+            td.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel, fp64 peak measured live
+    dom = measure_dominant_kernel(ctx, ffi)
+    try:
+        peak = measure_fp64_peak(local)
+        peak_src = "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 figure"
+    except Exception as e:  # noqa: BLE001
+        peak, peak_src = 35.5, f"fallback 35.5 TFLOP/s (cuBLAS DGEMM measured on this pool, profiles/); live measure failed: {e!r}"
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json")))
+        traffic = prof.get("dram_bytes_per_launch")
+    except Exception:  # noqa: BLE001
+        pass
+    flops_step = S * (N ** 3 / 3 + N * N * (P + 1) + 4 * N * P)
+    line = {
+        "metric": "gp_posteriors_per_s_N16384", "value": value, "unit": "posteriors/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "N": N, "d": d, "P": P, "kernel": w["kernel"], "draws_per_step": S,
+                   "outputs": "mean+diag var", "streams": args.streams, "parallelism": f"draw-parallel x{world}",
+                   "l2": "inputs larger than L2: each draw rebuilds and factors a 2 GiB K (L2 = 126 MB)"},
+        "wall_ms_per_step": wall_ms / args.steps,
+        "fp64_tflops_step": world * flops_step * args.steps / (dev_ms / 1e3) / 1e12,
+        "frac_of_chol_roofline_N3_3": (world * S * args.steps * N ** 3 / 3 / (dev_ms / 1e3) / 1e12) / (world * peak),
+        "frac_of_chol_roofline_2N3_3": (world * S * args.steps * 2 * N ** 3 / 3 / (dev_ms / 1e3) / 1e12) / (world * peak),
+        "e2e": {"value": e2e_value, "unit": "posteriors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
+                     "traffic": traffic, "kernel": "gemm_nt_kernel<128,128> (DMMA.8x8x4 SYRK, 8192x8192 k=8192 lower)",
+                     "flops_per_launch": dom["flops_per_launch"], "ms_per_launch": dom["ms"], "peak_source": peak_src},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if td is not None:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -827,3 +827,26 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     if (timing) *timing = ex->last;
     return B2GP_OK;
 }
+
+// ------------------------------------------------------------------------------------------ debug
+// Development aid (not part of include/b200gp.h): run the leaf kernel on a device block with per-phase
+// clock64 / globaltimer stamps.  prof_host receives 2*16 values (cycles, ns) per stamp.
+extern "C" int b2gp_debug_leaf(b2gp_ctx* ctx, int n, double* A_dev, int64_t lda, double* linv_dev, long long* prof_host) {
+    if (!ctx) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    RET_IF(ensure(ctx, ctx->d_info, 64 + 128 * 8));
+    int* dinfo = (int*)ctx->d_info.p;
+    long long* dprof = (long long*)((char*)ctx->d_info.p + 64);
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_info.p, 0, 64 + 128 * 8, st));
+    static bool attr = false;
+    if (!attr) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
+        attr = true;
+    }
+    potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, st>>>(A_dev, lda, n, linv_dev, dinfo, 0, dprof);
+    CUDA_TRY(ctx, cudaGetLastError());
+    CUDA_TRY(ctx, cudaMemcpyAsync(prof_host, dprof, 64 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return B2GP_OK;
+}

@@ -80,8 +80,8 @@ __device__ __forceinline__ void load_slice(double* sm, const double* __restrict_
     }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGNED>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_nt_kernel(const GemmArgs p) {
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, bool ALIGNED, int MINB>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) gemm_nt_kernel(const GemmArgs p) {
     constexpr int NT = WARPS_M * WARPS_N * 32;
     constexpr int WTM = BM / WARPS_M, WTN = BN / WARPS_N;
     constexpr int MI = WTM / 8, NI = WTN / 8;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, 1) gemm_nt_kernel(const
     }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
+template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES, int MINB>
 static int launch_gemm_cfg(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     constexpr int smem_bytes = STAGES * (BM + BN) * GEMM_LDS * (int)sizeof(double);
     const bool aligned = ((a.lda & 1) == 0) && ((a.ldb & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.A) & 15) == 0) &&
@@ -198,8 +198,8 @@ static int launch_gemm_cfg(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     a.tiles_n = (a.n + BN - 1) / BN;
     int64_t grid = a.lower_only ? (int64_t)a.tiles_m * (a.tiles_m + 1) / 2 : (int64_t)a.tiles_m * a.tiles_n;
     if (grid <= 0) return B2GP_OK;
-    auto kern = aligned ? gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true>
-                        : gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, false>;
+    auto kern = aligned ? gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true, MINB>
+                        : gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, false, MINB>;
     static bool attr_set[2] = {false, false};
     if (!attr_set[aligned ? 1 : 0]) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
@@ -231,5 +231,18 @@ static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t
     a.beta = beta;
     a.lower_only = lower_only ? 1 : 0;
     if (lower_only && m != n) return set_err(ctx, B2GP_ERR_ARG, "gemm_nt", "lower_only needs m == n", __FILE__, __LINE__);
-    return launch_gemm_cfg<128, 128, 2, 4, 4>(ctx, st, a);
+    // Tile choice.  A 128x128 tile keeps one SM busy for 128*128*k/64 cycles (DMMA: 64 fp64 FMA/clk/SM),
+    // i.e. ~17 us per k = 128, however few tiles there are; when the 128x128 grid would leave most of
+    // the 148 SMs idle, spend the same flops on more, smaller tiles.  The in-place triangular-solve
+    // use (C aliases A, n <= 128) needs a single column tile, which all three configurations give.
+    const int64_t tm128 = ceil_div(m, 128), tn128 = ceil_div(n, 128);
+    const int64_t t128 = lower_only ? tm128 * (tm128 + 1) / 2 : tm128 * tn128;
+    if (t128 >= 112) return launch_gemm_cfg<128, 128, 2, 4, 4, 1>(ctx, st, a);
+    if (lower_only) {
+        // square tiles only for the triangular tile map
+        return launch_gemm_cfg<64, 64, 2, 4, 4, 2>(ctx, st, a);
+    }
+    const int64_t t64 = ceil_div(m, 64) * tn128;
+    if (t64 >= 112) return launch_gemm_cfg<64, 128, 2, 4, 3, 2>(ctx, st, a);
+    return launch_gemm_cfg<32, 128, 1, 8, 3, 2>(ctx, st, a);
 }

@@ -16,178 +16,373 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 
-constexpr int PD_LD = 129;       // shared-memory stride of the 128x128 block
-constexpr int PD_ILD = 65;       // stride of the 64x64 inverse buffers
+// Short-latency 1/x and 1/sqrt(x) for the pivot chain of the diagonal block.  fp64 arithmetic has a
+// dependent-issue latency of ~30 cycles here, so the number of dependent operations is what counts:
+// the MUFU fp64 seeds (rcp/rsqrt.approx.ftz.f64, ~2^-20 relative) take one operation, and one cubic
+// step (error e -> ~e^3 <= 2^-60, i.e. rounding level) takes three:
+//     1/x:       e = 1 - x y;     y <- y + y (e + e^2)
+//     1/sqrt(x): e = 1 - x y^2;   y <- y + y e (1/2 + 3/8 e)
+// Non-positive / NaN pivots give NaN or Inf, which propagate as include/b200gp.h documents.
+__device__ __forceinline__ double pivot_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+__device__ __forceinline__ double pivot_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double xy = x * y;
+    const double e = fma(-xy, y, 1.0);
+    const double t = fma(0.375, e, 0.5);
+    return fma(y * e, t, y);
+}
+
+constexpr int PD_LD = 132;       // shared-memory stride: 132 % 32 == 4 -> DMMA fragment loads (8 rows x 32 B) conflict-free
 constexpr int PD_THREADS = 256;
-constexpr int PD_SMEM = (128 * PD_LD + 2 * 64 * PD_ILD) * (int)sizeof(double);
+constexpr int PD_SMEM = (128 * PD_LD + 32) * (int)sizeof(double);
 
 // One CTA factors the n x n (n <= 128) lower-triangular block at A in shared memory, writes L back
 // and writes inv(L) (lower, zero above the diagonal, leading dimension 128) to Linv.
+//
+//   for each 32-column panel b:
+//     (a) warp 0 factors the 32x32 diagonal block in REGISTERS (lane i owns row i; pivots and
+//         multipliers travel by warp shuffle), writes it to global, then inverts it in registers and
+//         leaves inv(D_b) in the block's place in shared memory;
+//     (b) all warps: panel rows below  X = A_panel * inv(D_b)^T      (DMMA, operands in shared memory)
+//     (c) all warps: trailing update   S22 -= X X^T on 8x8 tiles      (DMMA)
+//   then the inverse is assembled in place by the 2x2 block formula, two levels (32 -> 64 -> 128),
+//   four DMMA products with row / column ownership so that every product can overwrite its operand.
+//
 // A non-positive or NaN pivot records *info = index_base + j + 1 (first one wins) and lets NaNs
 // propagate; callers NaN-fill the outputs of that draw.
 __global__ void __launch_bounds__(PD_THREADS, 1)
-potrf_diag_kernel(double* __restrict__ A, int64_t lda, int n, double* __restrict__ Linv, int* info, int index_base) {
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int n, double* __restrict__ Linv, int* info, int index_base,
+                  long long* prof) {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;
-    double* I1 = sm + 128 * PD_LD;
-    double* I2 = I1 + 64 * PD_ILD;
+    double* RD = sm + 128 * PD_LD;  // reciprocal pivots of the current diagonal block
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const unsigned FULL = 0xffffffffu;
+    int pslot = 0;
+#define PD_PROF()                                                        \
+    do {                                                                 \
+        if (prof && tid == 0) {                                          \
+            long long gt_;                                               \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));      \
+            prof[2 * pslot] = clock64();                                 \
+            prof[2 * pslot + 1] = gt_;                                   \
+            ++pslot;                                                     \
+        }                                                                \
+    } while (0)
+    PD_PROF();
 
-    for (int idx = tid; idx < 128 * 128; idx += PD_THREADS) {
-        const int i = idx >> 7, j = idx & 127;
-        double v = 0.0;
-        if (i < n && j <= i) v = A[(int64_t)i * lda + j];
-        S[i * PD_LD + j] = v;
+    const bool gvec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    if (gvec) {
+        // 8192 double2 elements, 32 per thread, 8 loads in flight per thread
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = (it * 8 + u) * PD_THREADS + tid;
+                const int i = idx >> 6, j = (idx & 63) * 2;
+                v[u] = make_double2(0.0, 0.0);
+                if (i < n && j <= i) v[u] = *reinterpret_cast<const double2*>(A + (int64_t)i * lda + j);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = (it * 8 + u) * PD_THREADS + tid;
+                const int i = idx >> 6, j = (idx & 63) * 2;
+                if (j + 1 > i) v[u].y = 0.0;
+                *reinterpret_cast<double2*>(&S[i * PD_LD + j]) = v[u];
+            }
+        }
+    } else {
+        for (int idx = tid; idx < 128 * 128; idx += PD_THREADS) {
+            const int i = idx >> 7, j = idx & 127;
+            double v = 0.0;
+            if (i < n && j <= i) v = A[(int64_t)i * lda + j];
+            S[i * PD_LD + j] = v;
+        }
     }
     __syncthreads();
+    PD_PROF();
 
-    // ---- factorisation: 32-wide column panels, unblocked inside a panel, 4x4 register tiles for
-    //      the trailing update
-    for (int b0 = 0; b0 < n; b0 += 32) {
+    const int nb = (n + 31) >> 5;
+    for (int b = 0; b < nb; ++b) {
+        const int b0 = 32 * b;
         const int bw = min(32, n - b0);
-        const int bend = b0 + bw;
-        for (int j = b0; j < bend; ++j) {
-            const double piv = S[j * PD_LD + j];
-            if (!(piv > 0.0) && tid == 0) atomicCAS(info, 0, index_base + j + 1);
-            const double dj = sqrt(piv);
-            __syncthreads();  // everyone has read the pivot
-            if (tid == 0) S[j * PD_LD + j] = dj;
-            for (int i = j + 1 + tid; i < n; i += PD_THREADS) S[i * PD_LD + j] = S[i * PD_LD + j] / dj;
-            __syncthreads();
-            const int cols = bend - (j + 1);
-            const int rows = n - (j + 1);
-            if (cols > 0) {
-                for (int idx = tid; idx < rows * cols; idx += PD_THREADS) {
-                    const int i = j + 1 + idx / cols;
-                    const int k = j + 1 + idx % cols;
-                    if (k <= i) S[i * PD_LD + k] -= S[i * PD_LD + j] * S[k * PD_LD + j];
-                }
+        if (warp == 0) {
+            // ---- (a) 32x32 diagonal block in registers
+            double a[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) a[k] = S[(b0 + lane) * PD_LD + b0 + k];
+            if (lane >= bw) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) a[k] = (k == lane) ? 1.0 : 0.0;  // identity padding of a ragged block
             }
-            // (the next iteration's pivot read is ordered by the sync below)
-            __syncthreads();
-        }
-        const int R = n - bend;
-        if (R > 0) {
-            const int T = (R + 3) >> 2;
-            for (int mt = tid; mt < T * T; mt += PD_THREADS) {
-                const int tr = mt / T, tc = mt % T;
-                if (tc > tr) continue;
-                const int r0 = bend + 4 * tr, c0 = bend + 4 * tc;
-                double acc[4][4];
+            if (b == 0) PD_PROF();
+            // Unnormalised right-looking elimination: a[] holds the running Schur complement, the update
+            // of column k by column j is a[k] -= (a[j] / piv_j) * a_kj, so the per-column dependency chain is
+            //   shfl(piv) -> 1/piv (4 ops) -> a[j]/piv -> fma   and the rsqrt scaling of L is off the chain.
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
+            for (int j = 0; j < 32; ++j) {
+                const double piv = __shfl_sync(FULL, a[j], j);
+                if (!(piv > 0.0) && lane == 0 && j < bw) atomicCAS(info, 0, index_base + b0 + j + 1);
+                const double r = pivot_rcp(piv);
+                const double ajr = a[j] * r;
 #pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-                for (int c = b0; c < bend; ++c) {
-                    double a[4], b[4];
-#pragma unroll
-                    for (int x = 0; x < 4; ++x) a[x] = (r0 + x < n) ? S[(r0 + x) * PD_LD + c] : 0.0;
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) b[y] = (c0 + y < n) ? S[(c0 + y) * PD_LD + c] : 0.0;
-#pragma unroll
-                    for (int x = 0; x < 4; ++x)
-#pragma unroll
-                        for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+                for (int k = j + 1; k < 32; ++k) {
+                    const double akj = __shfl_sync(FULL, a[j], k);
+                    a[k] = fma(-ajr, akj, a[k]);
                 }
+                const double rs = pivot_rsqrt(piv);                 // 1 / L_jj
+                double sq = piv * rs;                               // L_jj = sqrt(piv), one Newton correction
+                sq = fma(fma(-sq, sq, piv), 0.5 * rs, sq);
+                a[j] = (lane == j) ? sq : a[j] * rs;
+                if (lane == j) RD[j] = rs;
+            }
+            if (b == 0) PD_PROF();
+            if (lane < bw) {
 #pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) {
-                        const int r = r0 + x, c = c0 + y;
-                        if (r < n && c <= r) S[r * PD_LD + c] -= acc[x][y];
+                for (int k = 0; k < 32; ++k)
+                    if (k <= lane) {
+                        A[(int64_t)(b0 + lane) * lda + b0 + k] = a[k];
+                        S[(b0 + lane) * PD_LD + b0 + k] = a[k];
                     }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (k <= lane) S[(b0 + lane) * PD_LD + b0 + k] = a[k];
+            }
+            __syncwarp();
+            if (b == 0) PD_PROF();
+            // inverse of the block: lane c computes column c by forward substitution, L broadcast from smem
+            double x[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < i; ++k) {
+                    const double l = S[(b0 + i) * PD_LD + b0 + k];
+                    if (k & 1)
+                        s1 = fma(l, x[k], s1);
+                    else
+                        s0 = fma(l, x[k], s0);
+                }
+                const double rdi = RD[i];
+                x[i] = (lane == i) ? rdi : -rdi * (s0 + s1);
+                if (i < lane) x[i] = 0.0;
+            }
+            __syncwarp();
+            if (b == 0) PD_PROF();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) S[(b0 + i) * PD_LD + b0 + lane] = x[i];
+        }
+        __syncthreads();
+        PD_PROF();
+        const int r_begin = b0 + 32;
+        if (r_begin < n) {
+            const int ntile = (n - r_begin + 7) >> 3;
+            // ---- (b) X = A_panel * inv(D)^T : X[r][c] = sum_k A[r][k] * Dinv[c][k]
+            for (int rt = warp; rt < ntile; rt += PD_THREADS / 32) {
+                const int r0 = r_begin + 8 * rt;
+                double af[8];
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) af[kk] = S[(r0 + g) * PD_LD + b0 + 4 * kk + t];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < 8; ++kk) {
+                        const double bb = S[(b0 + 8 * j + g) * PD_LD + b0 + 4 * kk + t];
+                        dmma884(c0, c1, af[kk], bb);
+                    }
+                    *reinterpret_cast<double2*>(&S[(r0 + g) * PD_LD + b0 + 8 * j + 2 * t]) = make_double2(c0, c1);
+                }
+            }
+            __syncthreads();
+            // ---- (c) trailing update on 8x8 tiles of the lower triangle
+            const int npairs = ntile * (ntile + 1) / 2;
+            // three tile pairs in flight per warp: DMMA accumulation chains are ~8 deep and slow to retire
+            for (int p0 = 3 * warp; p0 < npairs; p0 += 3 * (PD_THREADS / 32)) {
+                int r0[3], c0i[3];
+                double acc[3][2];
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int p = min(p0 + u, npairs - 1);
+                    int rt = 0;
+                    while ((rt + 1) * (rt + 2) / 2 <= p) ++rt;
+                    r0[u] = r_begin + 8 * rt;
+                    c0i[u] = r_begin + 8 * (p - rt * (rt + 1) / 2);
+                    acc[u][0] = acc[u][1] = 0.0;
+                }
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+#pragma unroll
+                    for (int u = 0; u < 3; ++u) {
+                        const double aa = S[(r0[u] + g) * PD_LD + b0 + 4 * kk + t];
+                        const double bb = S[(c0i[u] + g) * PD_LD + b0 + 4 * kk + t];
+                        dmma884(acc[u][0], acc[u][1], aa, bb);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    if (p0 + u < npairs) {
+                        double2* dst = reinterpret_cast<double2*>(&S[(r0[u] + g) * PD_LD + c0i[u] + 2 * t]);
+                        double2 old = *dst;
+                        old.x -= acc[u][0];
+                        old.y -= acc[u][1];
+                        *dst = old;
+                    }
+                }
             }
             __syncthreads();
         }
+        PD_PROF();
     }
 
-    // ---- write L back (lower triangle only)
-    for (int idx = tid; idx < 128 * 128; idx += PD_THREADS) {
-        const int i = idx >> 7, j = idx & 127;
-        if (i < n && j <= i) A[(int64_t)i * lda + j] = S[i * PD_LD + j];
+    // ---- write the off-diagonal-block part of L back (diagonal blocks went out in (a))
+    if (gvec) {
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            double2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = (it * 8 + u) * PD_THREADS + tid;
+                const int i = idx >> 6, j = (idx & 63) * 2;
+                v[u] = *reinterpret_cast<const double2*>(&S[i * PD_LD + j]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = (it * 8 + u) * PD_THREADS + tid;
+                const int i = idx >> 6, j = (idx & 63) * 2;
+                if (i < n && (j >> 5) < (i >> 5)) *reinterpret_cast<double2*>(A + (int64_t)i * lda + j) = v[u];
+            }
+        }
+    } else {
+        for (int idx = tid; idx < 128 * 128; idx += PD_THREADS) {
+            const int i = idx >> 7, j = idx & 127;
+            if (i < n && (j >> 5) < (i >> 5)) A[(int64_t)i * lda + j] = S[i * PD_LD + j];
+        }
     }
+    __syncthreads();
+    PD_PROF();
 
-    // ---- inverse of L by the 2x2 block formula  inv = [[I11, 0], [-I22 L21 I11, I22]]
-    const int n1 = min(n, 64), n2 = n - n1;
-    for (int idx = tid; idx < 2 * 64 * PD_ILD; idx += PD_THREADS) I1[idx] = 0.0;  // I1 and I2 are contiguous
-    __syncthreads();
-    if (tid < 64) {
-        const int j = tid;  // column j of inv(L11) by forward substitution
-        if (j < n1) {
-            for (int i = j; i < n1; ++i) {
-                double s = (i == j) ? 1.0 : 0.0;
-                for (int k = j; k < i; ++k) s = fma(-S[i * PD_LD + k], I1[k * PD_ILD + j], s);
-                I1[i * PD_ILD + j] = s / S[i * PD_LD + i];
-            }
-        }
-    } else if (tid < 128) {
-        const int j = tid - 64;  // column j of inv(L22)
-        if (j < n2) {
-            for (int i = j; i < n2; ++i) {
-                double s = (i == j) ? 1.0 : 0.0;
-                for (int k = j; k < i; ++k) s = fma(-S[(64 + i) * PD_LD + 64 + k], I2[k * PD_ILD + j], s);
-                I2[i * PD_ILD + j] = s / S[(64 + i) * PD_LD + 64 + i];
-            }
-        }
-    }
-    __syncthreads();
-    // T = L21 * I11  (n2 x n1), parked in the unused upper-right quadrant S[r][64 + c]
-    const int tr = tid >> 4, tc = tid & 15;
-    if (n2 > 0) {
-        double acc[4][4];
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-        for (int k = 4 * tc; k < n1; ++k) {
-            double a[4], b[4];
-#pragma unroll
-            for (int x = 0; x < 4; ++x) a[x] = S[(64 + 4 * tr + x) * PD_LD + k];  // rows >= n are zero
-#pragma unroll
-            for (int y = 0; y < 4; ++y) b[y] = I1[k * PD_ILD + 4 * tc + y];
-#pragma unroll
-            for (int x = 0; x < 4; ++x)
-#pragma unroll
-                for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
-        }
-#pragma unroll
-        for (int x = 0; x < 4; ++x)
-#pragma unroll
-            for (int y = 0; y < 4; ++y) S[(4 * tr + x) * PD_LD + 64 + 4 * tc + y] = acc[x][y];
-    }
-    __syncthreads();
-    // I21 = -I22 * T  and the final store of the whole inverse (leading dimension 128)
+    // ---- inverse assembly, level 1: the two 64-blocks.  M = -P1 * (L10 * P0), in place of L10.
     {
-        double acc[4][4];
+        const int base = 64 * (warp >> 2);
+        const int q = warp & 3;
+        // step 1: T = L10 * P0   (row ownership: this warp owns rows r0..r0+7 of T)
+        {
+            const int r0 = base + 32 + 8 * q;
+            double af[8];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+            for (int kk = 0; kk < 8; ++kk) af[kk] = S[(r0 + g) * PD_LD + base + 4 * kk + t];
+            __syncwarp();
 #pragma unroll
-            for (int y = 0; y < 4; ++y) acc[x][y] = 0.0;
-        if (n2 > 0) {
-            const int kmax = min(4 * tr + 4, n2);
-            for (int k = 0; k < kmax; ++k) {
-                double a[4], b[4];
+            for (int j = 0; j < 4; ++j) {
+                double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-                for (int x = 0; x < 4; ++x) a[x] = I2[(4 * tr + x) * PD_ILD + k];
-#pragma unroll
-                for (int y = 0; y < 4; ++y) b[y] = S[k * PD_LD + 64 + 4 * tc + y];
-#pragma unroll
-                for (int x = 0; x < 4; ++x)
-#pragma unroll
-                    for (int y = 0; y < 4; ++y) acc[x][y] = fma(a[x], b[y], acc[x][y]);
+                for (int kk = 0; kk < 8; ++kk) {
+                    if (kk < 2 * j) continue;  // P0 is lower triangular: rows k < 8j of this column tile are zero
+                    const double bb = S[(base + 4 * kk + t) * PD_LD + base + 8 * j + g];
+                    dmma884(c0, c1, af[kk], bb);
+                }
+                *reinterpret_cast<double2*>(&S[(r0 + g) * PD_LD + base + 8 * j + 2 * t]) = make_double2(c0, c1);
             }
         }
+        __syncthreads();
+        // step 2: M10 = -P1 * T   (column ownership: this warp owns columns c0..c0+7)
+        {
+            const int c0i = base + 8 * q;
+            double bf[8];
 #pragma unroll
-        for (int x = 0; x < 4; ++x)
+            for (int kk = 0; kk < 8; ++kk) bf[kk] = S[(base + 32 + 4 * kk + t) * PD_LD + c0i + g];
+            __syncwarp();
 #pragma unroll
-            for (int y = 0; y < 4; ++y) {
-                const int r = 4 * tr + x, c = 4 * tc + y;
-                Linv[(int64_t)r * 128 + c] = I1[r * PD_ILD + c];                // I11
-                Linv[(int64_t)r * 128 + 64 + c] = 0.0;                           // upper right
-                Linv[(int64_t)(64 + r) * 128 + c] = -acc[x][y];                  // I21
-                Linv[(int64_t)(64 + r) * 128 + 64 + c] = I2[r * PD_ILD + c];    // I22
+            for (int i = 0; i < 4; ++i) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    if (kk > 2 * i + 1) continue;  // P1 lower triangular: k <= r
+                    const double aa = S[(base + 32 + 8 * i + g) * PD_LD + base + 32 + 4 * kk + t];
+                    dmma884(c0, c1, aa, bf[kk]);
+                }
+                *reinterpret_cast<double2*>(&S[(base + 32 + 8 * i + g) * PD_LD + c0i + 2 * t]) = make_double2(-c0, -c1);
             }
+        }
+        __syncthreads();
     }
+    // ---- level 2: M_BA = -I_B * (L_BA * I_A) with I_A = S[0:64,0:64], I_B = S[64:128,64:128], L_BA = S[64:128,0:64]
+    {
+        // step 3: T2 = L_BA * I_A   (row ownership)
+        {
+            const int r0 = 64 + 8 * warp;
+            double af[16];
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) af[kk] = S[(r0 + g) * PD_LD + 4 * kk + t];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) {
+                    if (kk < 2 * j) continue;
+                    const double bb = S[(4 * kk + t) * PD_LD + 8 * j + g];
+                    dmma884(c0, c1, af[kk], bb);
+                }
+                *reinterpret_cast<double2*>(&S[(r0 + g) * PD_LD + 8 * j + 2 * t]) = make_double2(c0, c1);
+            }
+        }
+        __syncthreads();
+        // step 4: M_BA = -I_B * T2   (column ownership)
+        {
+            const int c0i = 8 * warp;
+            double bf[16];
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) bf[kk] = S[(64 + 4 * kk + t) * PD_LD + c0i + g];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) {
+                    if (kk > 2 * i + 1) continue;
+                    const double aa = S[(64 + 8 * i + g) * PD_LD + 64 + 4 * kk + t];
+                    dmma884(c0, c1, aa, bf[kk]);
+                }
+                *reinterpret_cast<double2*>(&S[(64 + 8 * i + g) * PD_LD + c0i + 2 * t]) = make_double2(-c0, -c1);
+            }
+        }
+        __syncthreads();
+    }
+    PD_PROF();
+#pragma unroll 1
+    for (int it = 0; it < 4; ++it) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = (it * 8 + u) * PD_THREADS + tid;
+            const int i = idx >> 6, j = (idx & 63) * 2;
+            v[u] = *reinterpret_cast<const double2*>(&S[i * PD_LD + j]);
+            if (j > i) v[u].x = 0.0;
+            if (j + 1 > i) v[u].y = 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = (it * 8 + u) * PD_THREADS + tid;
+            *reinterpret_cast<double2*>(Linv + 2 * (int64_t)idx) = v[u];
+        }
+    }
+    __syncthreads();
+    PD_PROF();
+#undef PD_PROF
 }
 
 static int potrf_diag(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int n, double* Linv_blk, int* info,
@@ -197,7 +392,7 @@ static int potrf_diag(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, in
         CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
         attr = true;
     }
-    potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, st>>>(A, lda, n, Linv_blk, info, index_base);
+    potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, st>>>(A, lda, n, Linv_blk, info, index_base, nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return B2GP_OK;
