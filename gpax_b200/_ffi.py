@@ -66,6 +66,14 @@ SIGNATURES = {
                                  C.POINTER(Timing)]),
     "b2gp_sparse_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int,
                                         _vp, C.c_int, C.c_double, C.c_uint, _vp, _vp, _vp, _vp, C.POINTER(Timing)]),
+    "b2gp_sparse_partial": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp,
+                                      C.c_int64, _vp, _ip]),
+    "b2gp_sparse_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int,
+                                     C.c_double, C.c_uint, _vp, _vp, _vp, _ip]),
+    "b2gp_potrf_inv": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _ip]),
+    "b2gp_trsm_inv": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64]),
+    "b2gp_rowdot": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _vp, _vp, C.c_int]),
+    "b2gp_copy2d": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64]),
 }
 
 _lib = None

@@ -700,6 +700,84 @@ __global__ void scale_by_inv_noise_kernel(double* v, int64_t n, const double* th
     if (i < n) v[i] = v[i] / theta[d + 1];
 }
 
+// Partial Nystrom statistics of a shard of the training set (all device pointers):
+//   Luu = chol(Kuu + jitter I), W = Luu^{-1} K(Xu, Xtr_shard),  Kpart = W W^T / noise (lower),  cpart = W y / noise.
+// Summed over shards these are the K (before "+ I") and W D^{-1} y of sparse_gp.py:198-204.
+static int sparse_partial_dev(b2gp_ctx* ctx, Slot& sl, int kind, const double* dXu, int64_t M, const double* dXtr, int64_t N,
+                              const double* dy, int d, const double* dth, double jitter, double noise_h, double* Luu, int64_t ldM,
+                              double* LinvU, double* Kpart, int64_t ldk, double* cpart, int* dinfo) {
+    cudaStream_t st = sl.stream;
+    const int64_t ldN = round_up(N, 8);
+    RET_IF(ensure(ctx, sl.Vt, (size_t)N * ldM * 8));
+    RET_IF(ensure(ctx, sl.cov, (size_t)M * ldN * 8));
+    double* Wt = (double*)sl.Vt.p;
+    double* W = (double*)sl.cov.p;
+    // Kuu = kernel(Xu, Xu, params, **kwargs): noise defaults to 0, so the diagonal gets jitter only (sparse_gp.py:193)
+    RET_IF(launch_gram(ctx, st, kind, dXu, M, dXu, M, d, dth, 0.0, jitter, 1, 1, Luu, ldM));
+    RET_IF(potrf_rec(ctx, st, Luu, ldM, M, LinvU, dinfo, 0));                                   // sparse_gp.py:194
+    // W^T = K_fu Luu^{-T}  (W = Luu^{-1} Kuf, sparse_gp.py:195-197), one training point per row
+    RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wt, ldM));
+    RET_IF(trsm_rec(ctx, st, Wt, ldM, N, Luu, ldM, M, LinvU));
+    {
+        dim3 g((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32)), b(32, 8);
+        transpose_kernel<<<g, b, 0, st>>>(W, ldN, Wt, ldM, N, M);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    // W D^{-1} W^T with D = noise * 1  (sparse_gp.py:198-199); 1/noise applied after the sum
+    RET_IF(gemm_nt(ctx, st, M, M, N, 1.0 / noise_h, W, ldN, W, ldN, 0.0, Kpart, ldk, true));
+    // W D^{-1} y  (sparse_gp.py:203-204)
+    rowdot2_kernel<<<(unsigned)M, RD_THREADS, 0, st>>>(W, ldN, N, dy, 1.0 / noise_h, cpart, nullptr);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return B2GP_OK;
+}
+
+// Posterior from the summed statistics: K = Ksum + I, L = chol(K), then sparse_gp.py:206-217.
+static int sparse_finish_dev(b2gp_ctx* ctx, Slot& sl, int kind, const double* dXu, int64_t M, const double* Luu, int64_t ldM,
+                             const double* LinvU, double* Kmat, int64_t ldk, double* LinvK, const double* cvec,
+                             const double* dXnew, int64_t P, int d, const double* dth, int noiseless, double jitter,
+                             bool want_var, bool want_cov, double* dmean, double* dvar, double* C, int64_t ldc, int* dinfo) {
+    cudaStream_t st = sl.stream;
+    RET_IF(ensure(ctx, sl.LinvC, (size_t)2 * (P + 1) * ldM * 8));
+    RET_IF(ensure(ctx, sl.misc, (size_t)(2 * P + 16) * 8));
+    double* Wst = (double*)sl.LinvC.p;          // P x ldM          Ws^T = K_su Luu^{-T}
+    double* R = Wst + (P + 1) * ldM;            // (P+1) x ldM      rows 0..P-1: (L^{-1} Ws)^T; row P: L^{-1} c
+    double* qv = (double*)sl.misc.p;            // |Ws^T[p]|^2
+    double* rv = qv + P;                        // |R[p]|^2
+    add_diag_kernel<<<grid_for(M), 256, 0, st>>>(Kmat, ldk, M, 1.0);                            // sparse_gp.py:200
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    RET_IF(potrf_rec(ctx, st, Kmat, ldk, M, LinvK, dinfo + 1, 0));                              // sparse_gp.py:201
+    // Ws^T = K_su Luu^{-T}  (sparse_gp.py:206-207)
+    RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wst, ldM));
+    RET_IF(trsm_rec(ctx, st, Wst, ldM, P, Luu, ldM, M, LinvU));
+    // pack = [c | Ws]; L^{-1} pack  (sparse_gp.py:208-212)
+    copy2d_kernel<<<grid_for(P * M), 256, 0, st>>>(R, ldM, Wst, ldM, P, M);
+    CUDA_TRY(ctx, cudaMemcpyAsync(R + P * ldM, cvec, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+    ctx->launches++;
+    RET_IF(trsm_rec(ctx, st, R, ldM, P + 1, Kmat, ldk, M, LinvK));
+    // mean = (L^{-1} c)^T (L^{-1} Ws)  (sparse_gp.py:213)
+    rowdot2_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(R, ldM, M, R + P * ldM, 1.0, dmean, rv);
+    rowdot2_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(Wst, ldM, M, nullptr, 1.0, nullptr, qv);
+    sparse_var_kernel<<<grid_for(P), 256, 0, st>>>(want_var ? dvar : nullptr, dmean, qv, rv, P, kind, d, dth,
+                                                   noiseless ? 0.0 : 1.0, jitter, dinfo, dinfo + 1);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 3;
+    if (want_cov) {
+        // cov = Kss - Ws^T Ws + (L^{-1}Ws)^T (L^{-1}Ws)  (sparse_gp.py:215-217)
+        RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXnew, P, d, dth, noiseless ? 0.0 : 1.0, jitter, 1, 1, C, ldc));
+        RET_IF(gemm_nt(ctx, st, P, P, M, -1.0, Wst, ldM, Wst, ldM, 1.0, C, ldc, true));
+        RET_IF(gemm_nt(ctx, st, P, P, M, 1.0, R, ldM, R, ldM, 1.0, C, ldc, true));
+        dim3 g2((unsigned)ceil_div(P, 32), (unsigned)ceil_div(P, 32)), b2(32, 32);
+        mirror_lower_kernel<<<g2, b2, 0, st>>>(C, ldc, P);
+        nan_if_bad_kernel<<<grid_for(P * P), 256, 0, st>>>(C, ldc, P, P, dinfo, dinfo + 1);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 2;
+    }
+    return B2GP_OK;
+}
+
 extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* Xtr, int64_t N,
                                      const double* yres, const double* Xnew, int64_t P, int d, const double* theta, int noiseless,
                                      double jitter, unsigned flags, double* mean, double* var, double* cov, int* info,
@@ -726,93 +804,37 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     RET_IF(stage_in(ctx, st, ctx->d_in[2], Xnew, (size_t)P * d * 8, dev, &dXnew));
     RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, dev, &dth));
     RET_IF(stage_in(ctx, st, ctx->d_in[5], Xu, (size_t)M * d * 8, dev, &dXu));
-
-    const int64_t ldM = round_up(M, 8), ldN = round_up(N, 8), ldC = round_up(P, 8);
-    // workspaces (slot 0): A <- Kuu/Luu (M x ldM) and Kmat/L (M x ldM); Vt <- Wt (N x ldM); cov buffer <- W (M x ldN)
+    double noise_h = 0.0;
+    if (dev) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(&noise_h, dth + d + 1, 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    } else {
+        noise_h = theta[d + 1];
+    }
+    const int64_t ldM = round_up(M, 8), ldC = round_up(P, 8);
     RET_IF(ensure(ctx, sl.A, (size_t)2 * M * ldM * 8));
-    RET_IF(ensure(ctx, sl.Vt, (size_t)N * ldM * 8));
-    RET_IF(ensure(ctx, sl.cov, (size_t)M * ldN * 8));
     RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
-    RET_IF(ensure(ctx, sl.LinvC, (size_t)2 * (P + 1) * ldM * 8 + (size_t)P * ldC * 8));
-    RET_IF(ensure(ctx, sl.misc, (size_t)(4 * P + 2 * M + 16) * 8));
+    RET_IF(ensure(ctx, ctx->d_out[0], (size_t)(2 * P + M + 16) * 8));
+    if (want_cov && !dev) RET_IF(ensure(ctx, ctx->d_out[2], (size_t)P * ldC * 8));
     RET_IF(ensure(ctx, ctx->d_info, 64));
     int* dinfo = (int*)ctx->d_info.p;
     CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
     double* Luu = (double*)sl.A.p;
     double* Kmat = Luu + M * ldM;
-    double* Wt = (double*)sl.Vt.p;
-    double* W = (double*)sl.cov.p;
     double* LinvU = (double*)sl.Linv.p;
     double* LinvK = LinvU + linv_bytes(M) / 8;
-    double* Wst = (double*)sl.LinvC.p;          // (P) x ldM        Ws^T = K_su Luu^{-T}
-    double* R = Wst + (P + 1) * ldM;            // (P+1) x ldM      rows 0..P-1: Ws^T then (L^{-1} Ws)^T; row P: c then L^{-1} c
-    double* Cb = R + (P + 1) * ldM;             // P x ldC          covariance staging (host mode)
-    double* qv = (double*)sl.misc.p;            // |Ws^T[p]|^2
-    double* rv = qv + P;                        // |R[p]|^2
-    double* mv = rv + P;                        // mean staging
-    double* vv = mv + P;                        // var staging
-    double* cvec = vv + P;                      // W D^-1 y (M)
-
-    // Kuu = kernel(Xu, Xu, params, **kwargs): noise defaults to 0, so the diagonal gets jitter only (sparse_gp.py:193)
-    RET_IF(launch_gram(ctx, st, kind, dXu, M, dXu, M, d, dth, 0.0, jitter, 1, 1, Luu, ldM));
-    RET_IF(potrf_rec(ctx, st, Luu, ldM, M, LinvU, dinfo, 0));                                   // sparse_gp.py:194
-    // W^T = K_fu Luu^{-T}  (W = Luu^{-1} Kuf, sparse_gp.py:195-197), one training point per row
-    RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wt, ldM));
-    RET_IF(trsm_rec(ctx, st, Wt, ldM, N, Luu, ldM, M, LinvU));
-    {
-        dim3 g((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32)), b(32, 8);
-        transpose_kernel<<<g, b, 0, st>>>(W, ldN, Wt, ldM, N, M);
-        CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches++;
-    }
-    // K = W D^{-1} W^T + I with D = noise * 1  (sparse_gp.py:198-200); 1/noise applied after the sum
-    {
-        double noise_h = 0.0;
-        if (dev)
-            CUDA_TRY(ctx, cudaMemcpyAsync(&noise_h, dth + d + 1, 8, cudaMemcpyDeviceToHost, st));
-        else
-            noise_h = theta[d + 1];
-        if (dev) CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        RET_IF(gemm_nt(ctx, st, M, M, N, 1.0 / noise_h, W, ldN, W, ldN, 0.0, Kmat, ldM, true));
-    }
-    add_diag_kernel<<<grid_for(M), 256, 0, st>>>(Kmat, ldM, M, 1.0);
-    CUDA_TRY(ctx, cudaGetLastError());
-    RET_IF(potrf_rec(ctx, st, Kmat, ldM, M, LinvK, dinfo + 1, 0));                              // sparse_gp.py:201
-    // c = W D^{-1} y  (sparse_gp.py:203-204)
-    rowdot2_kernel<<<(unsigned)M, RD_THREADS, 0, st>>>(W, ldN, N, dy, 1.0, cvec, nullptr);
-    scale_by_inv_noise_kernel<<<grid_for(M), 256, 0, st>>>(cvec, M, dth, d);
-    CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 3;
-    // Ws^T = K_su Luu^{-T}  (sparse_gp.py:206-207)
-    RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wst, ldM));
-    RET_IF(trsm_rec(ctx, st, Wst, ldM, P, Luu, ldM, M, LinvU));
-    // pack = [c | Ws]; L^{-1} pack  (sparse_gp.py:208-212)
-    copy2d_kernel<<<grid_for(P * M), 256, 0, st>>>(R, ldM, Wst, ldM, P, M);
-    CUDA_TRY(ctx, cudaMemcpyAsync(R + P * ldM, cvec, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
-    ctx->launches++;
-    RET_IF(trsm_rec(ctx, st, R, ldM, P + 1, Kmat, ldM, M, LinvK));
-    // mean = (L^{-1} c)^T (L^{-1} Ws)  (sparse_gp.py:213)
-    double* dmean = want_mean ? (dev ? mean : mv) : mv;
-    double* dvar = want_var ? (dev ? var : vv) : nullptr;
-    rowdot2_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(R, ldM, M, R + P * ldM, 1.0, dmean, rv);
-    rowdot2_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(Wst, ldM, M, nullptr, 1.0, nullptr, qv);
-    sparse_var_kernel<<<grid_for(P), 256, 0, st>>>(dvar, dmean, qv, rv, P, kind, d, dth, noiseless ? 0.0 : 1.0, jitter, dinfo, dinfo + 1);
-    CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += 3;
-    if (want_cov) {
-        // cov = Kss - Ws^T Ws + (L^{-1}Ws)^T (L^{-1}Ws)  (sparse_gp.py:215-217)
-        double* C = dev ? cov : Cb;
-        const int64_t ldc = dev ? P : ldC;
-        RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXnew, P, d, dth, noiseless ? 0.0 : 1.0, jitter, 1, 1, C, ldc));
-        RET_IF(gemm_nt(ctx, st, P, P, M, -1.0, Wst, ldM, Wst, ldM, 1.0, C, ldc, true));
-        RET_IF(gemm_nt(ctx, st, P, P, M, 1.0, R, ldM, R, ldM, 1.0, C, ldc, true));
-        dim3 g2((unsigned)ceil_div(P, 32), (unsigned)ceil_div(P, 32)), b2(32, 32);
-        mirror_lower_kernel<<<g2, b2, 0, st>>>(C, ldc, P);
-        nan_if_bad_kernel<<<grid_for(P * P), 256, 0, st>>>(C, ldc, P, P, dinfo, dinfo + 1);
-        CUDA_TRY(ctx, cudaGetLastError());
-        ctx->launches += 2;
-        if (!dev) CUDA_TRY(ctx, cudaMemcpy2DAsync(cov, (size_t)P * 8, C, (size_t)ldc * 8, (size_t)P * 8, (size_t)P, cudaMemcpyDeviceToHost, st));
-    }
+    double* mv = (double*)ctx->d_out[0].p;
+    double* vv = mv + P;
+    double* cvec = vv + P;
+    RET_IF(sparse_partial_dev(ctx, sl, kind, dXu, M, dXtr, N, dy, d, dth, jitter, noise_h, Luu, ldM, LinvU, Kmat, ldM, cvec, dinfo));
+    double* dmean = (want_mean && dev) ? mean : mv;
+    double* dvar = (want_var && dev) ? var : vv;
+    double* C = dev ? cov : (double*)ctx->d_out[2].p;
+    const int64_t ldc = dev ? P : ldC;
+    RET_IF(sparse_finish_dev(ctx, sl, kind, dXu, M, Luu, ldM, LinvU, Kmat, ldM, LinvK, cvec, dXnew, P, d, dth, noiseless, jitter,
+                             want_var, want_cov, dmean, dvar, C, ldc, dinfo));
+    if (want_cov && !dev)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(cov, (size_t)P * 8, C, (size_t)ldc * 8, (size_t)P * 8, (size_t)P, cudaMemcpyDeviceToHost, st));
     int hinfo[2] = {0, 0};
     CUDA_TRY(ctx, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (!dev) {
@@ -825,6 +847,140 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     ex->last.flops = 2.0 * m * m * m / 3.0 + 2.0 * m * m * n + 2.0 * m * m * (p + 1.0) + (want_cov ? 2.0 * m * p * p : 0.0);
     ex->last.gram_bytes = 8.0 * (m * n + m * m / 2.0 + m * p);
     if (timing) *timing = ex->last;
+    return B2GP_OK;
+}
+
+// ---- sharded sparse path ("N-sharded sparse GP"): each rank calls _partial on its shard of
+// the training set, the M x M matrix and the M-vector are summed across ranks (NCCL all-reduce by the caller),
+// every rank calls _finish.  All array pointers are DEVICE pointers; theta is a HOST pointer (d+3 values).
+extern "C" int b2gp_sparse_partial(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* Xtr, int64_t N,
+                                   const double* yres, int d, const double* theta, double jitter, double* Kpart, int64_t ldk,
+                                   double* cpart, int* info) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xu && Xtr && yres && theta && Kpart && cpart && info);
+    ARG_CHECK(ctx, M >= 1 && N >= 1 && d >= 1 && d <= GRAM_MAX_D && ldk >= M);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const double* dth;
+    RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)(d + 3) * 8, false, &dth));
+    const int64_t ldM = round_up(M, 8);
+    RET_IF(ensure(ctx, sl.A, (size_t)2 * M * ldM * 8));
+    RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
+    RET_IF(sparse_partial_dev(ctx, sl, kind, Xu, M, Xtr, N, yres, d, dth, jitter, theta[d + 1], (double*)sl.A.p, ldM,
+                              (double*)sl.Linv.p, Kpart, ldk, cpart, dinfo));
+    CUDA_TRY(ctx, cudaMemcpyAsync(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return tm.end(st, nullptr);
+}
+
+extern "C" int b2gp_sparse_finish(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, double* Ksum, int64_t ldk,
+                                  const double* csum, const double* Xnew, int64_t P, int d, const double* theta, int noiseless,
+                                  double jitter, unsigned flags, double* mean, double* var, double* cov, int* info) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xu && Ksum && csum && Xnew && theta && mean && info);
+    ARG_CHECK(ctx, M >= 1 && P >= 1 && d >= 1 && d <= GRAM_MAX_D && ldk >= M);
+    const bool want_var = flags & B2GP_OUT_VAR, want_cov = flags & B2GP_OUT_COV;
+    ARG_CHECK(ctx, !want_var || var);
+    ARG_CHECK(ctx, !want_cov || cov);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const double* dth;
+    RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)(d + 3) * 8, false, &dth));
+    const int64_t ldM = round_up(M, 8);
+    RET_IF(ensure(ctx, sl.A, (size_t)2 * M * ldM * 8));
+    RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
+    double* Luu = (double*)sl.A.p;
+    double* LinvU = (double*)sl.Linv.p;
+    double* LinvK = LinvU + linv_bytes(M) / 8;
+    // Luu is rebuilt here (M^3/3 flops) so that _finish does not depend on ctx state left by _partial
+    RET_IF(launch_gram(ctx, st, kind, Xu, M, Xu, M, d, dth, 0.0, jitter, 1, 1, Luu, ldM));
+    RET_IF(potrf_rec(ctx, st, Luu, ldM, M, LinvU, dinfo, 0));
+    RET_IF(sparse_finish_dev(ctx, sl, kind, Xu, M, Luu, ldM, LinvU, Ksum, ldk, LinvK, csum, Xnew, P, d, dth, noiseless, jitter,
+                             want_var, want_cov, mean, var, cov, P, dinfo));
+    int hinfo[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    info[0] = hinfo[0] != 0 ? hinfo[0] : -hinfo[1];
+    return B2GP_OK;
+}
+
+// ---- building blocks of the block-cyclic multi-GPU factorisation (device pointers only)
+// Factor an n x n block and export its inverted 128x128 diagonal blocks (ceil(n/128) * 128*128 doubles) to Linv_out.
+extern "C" int b2gp_potrf_inv(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, double* Linv_out, int* info) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, A && Linv_out && info && n >= 1 && lda >= n);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_info.p, 0, 8, st));
+    RET_IF(potrf_rec(ctx, st, A, lda, n, Linv_out, (int*)ctx->d_info.p, 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(info, ctx->d_info.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    return tm.end(st, nullptr);
+}
+
+// B (nrhs rows of length n) <- B L^{-T} with the inverted diagonal blocks supplied by the caller
+extern "C" int b2gp_trsm_inv(b2gp_ctx* ctx, int64_t n, int64_t nrhs, const double* L, int64_t ldl, const double* Linv,
+                             double* B, int64_t ldb) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, L && Linv && B && n >= 1 && nrhs >= 0 && ldl >= n && ldb >= n);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    RET_IF(trsm_rec(ctx, st, B, ldb, nrhs, L, ldl, n, Linv));
+    return tm.end(st, nullptr);
+}
+
+// dot[r] (+)= scale * <R[r, 0:len), w>,  nrm[r] (+)= |R[r, 0:len)|^2   (either output may be NULL)
+__global__ void accumulate_kernel(double* dst, const double* src, int64_t n, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = accumulate ? dst[i] + src[i] : src[i];
+}
+extern "C" int b2gp_rowdot(b2gp_ctx* ctx, int64_t rows, int64_t len, const double* R, int64_t ldr, const double* w,
+                           double scale, double* dot, double* nrm, int accumulate) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, R && rows >= 0 && len >= 0 && ldr >= len && (dot == nullptr || w != nullptr));
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    if (rows > 0) {
+        RET_IF(ensure(ctx, ctx->slots[0].misc, (size_t)(2 * rows + 16) * 8));
+        double* t1 = (double*)ctx->slots[0].misc.p;
+        double* t2 = t1 + rows;
+        rowdot2_kernel<<<(unsigned)rows, RD_THREADS, 0, st>>>(R, ldr, len, w, scale, dot ? t1 : nullptr, nrm ? t2 : nullptr);
+        if (dot) accumulate_kernel<<<grid_for(rows), 256, 0, st>>>(dot, t1, rows, accumulate);
+        if (nrm) accumulate_kernel<<<grid_for(rows), 256, 0, st>>>(nrm, t2, rows, accumulate);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 3;
+    }
+    return tm.end(st, nullptr);
+}
+
+extern "C" int b2gp_copy2d(b2gp_ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, dst && src && rows >= 0 && cols >= 0 && ldd >= cols && lds >= cols);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    if (rows && cols)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)cols * 8, (size_t)rows,
+                                        cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
     return B2GP_OK;
 }
 

@@ -158,6 +158,34 @@ int  b2gp_sparse_posterior(b2gp_ctx* ctx, int kind,
                            double* mean, double* var, double* cov,
                            int* info, b2gp_timing* timing);
 
+/* ---- multi-GPU building blocks.  One process per GPU; the exchange steps
+ * (panel broadcast, M x M all-reduce) are issued by the host side over NCCL on these same device
+ * buffers (gpax_b200/distributed.py).  All array pointers below are DEVICE pointers. ----------------*/
+
+/* N-sharded sparse posterior: per-shard statistics, then the posterior from their sum.
+ *   Kpart[M,M] (lower) = W W^T / noise,  cpart[M] = W y / noise  with W = Luu^{-1} K(Xu, Xtr_shard)
+ *   (gpax/models/sparse_gp.py:193-199, 203-204 restricted to a shard; sums over shards give the full terms).
+ *   theta is a HOST pointer (d+3 values).                                                           */
+int  b2gp_sparse_partial(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* Xtr, int64_t N,
+                         const double* yres, int d, const double* theta, double jitter,
+                         double* Kpart, int64_t ldk, double* cpart, int* info);
+/* Ksum is overwritten (+I, then its Cholesky factor): sparse_gp.py:200-217.                          */
+int  b2gp_sparse_finish(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, double* Ksum, int64_t ldk,
+                        const double* csum, const double* Xnew, int64_t P, int d, const double* theta,
+                        int noiseless, double jitter, unsigned flags,
+                        double* mean, double* var, double* cov, int* info);
+
+/* Block-cyclic Cholesky: factor one diagonal block and export the inverted 128x128 sub-blocks
+ * (ceil(n/128)*128*128 doubles) so that panel solves can run later / on other blocks.              */
+int  b2gp_potrf_inv(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, double* Linv_out, int* info);
+/* B (nrhs rows of length n, leading dimension ldb) <- B L^{-T} using Linv from b2gp_potrf_inv.      */
+int  b2gp_trsm_inv(b2gp_ctx* ctx, int64_t n, int64_t nrhs, const double* L, int64_t ldl,
+                   const double* Linv, double* B, int64_t ldb);
+/* dot[r] (+)= scale * <R[r,0:len), w>,  nrm[r] (+)= |R[r,0:len)|^2 ; either output may be NULL.      */
+int  b2gp_rowdot(b2gp_ctx* ctx, int64_t rows, int64_t len, const double* R, int64_t ldr, const double* w,
+                 double scale, double* dot, double* nrm, int accumulate);
+int  b2gp_copy2d(b2gp_ctx* ctx, double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols);
+
 #ifdef __cplusplus
 }
 #endif
