@@ -66,6 +66,7 @@ SIGNATURES = {
                                  C.POINTER(Timing)]),
     "b2gp_sparse_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int,
                                         _vp, C.c_int, C.c_double, C.c_uint, _vp, _vp, _vp, _vp, C.POINTER(Timing)]),
+    "b2gp_mll": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, C.c_uint, _dp, _vp, _vp, _ip]),
     "b2gp_sparse_partial": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp,
                                       C.c_int64, _vp, _ip]),
     "b2gp_sparse_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int,
@@ -282,6 +283,19 @@ class Context:
         if timing:
             out["timing"] = t.as_dict()
         return out
+
+    def mll(self, kind, X, yres, theta, jitter=1e-6, want_grad=True, want_alpha=False):
+        """log marginal likelihood, its gradient w.r.t. log(lengthscale[d], k_scale, noise, period), alpha = K^-1 y"""
+        X, yres = _f64(X), _f64(yres)
+        N, d = X.shape
+        theta = _f64(theta).reshape(d + 3)
+        val = C.c_double(0.0)
+        grad = np.zeros(d + 3) if want_grad else None
+        alpha = np.zeros(N) if want_alpha else None
+        info = C.c_int(0)
+        self._check(self.lib.b2gp_mll(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), N, _ptr(yres), d,
+                                      _ptr(theta), float(jitter), 0, C.byref(val), _ptr(grad), _ptr(alpha), C.byref(info)))
+        return val.value, grad, alpha, info.value
 
     def sparse_posterior(self, kind, Xu, Xtr, yres, Xnew, theta, noiseless=False, jitter=1e-6, want=("mean", "cov")):
         Xu, Xtr, Xnew = _f64(Xu), _f64(Xtr), _f64(Xnew)

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "gram.cuh"
+#include "mll.cuh"
 #include "posterior.cuh"
 #include "potrf.cuh"
 
@@ -39,6 +40,18 @@ struct Extra {  // ctx-private state that is not part of the struct the kernels'
     DevBuf potrf_buf;  // staging for host-pointer b2gp_potrf / trsm / gemm
     DevBuf gemm_buf[3];
     std::vector<void*> user_allocs;
+    // factor cache of slot 0 (host-pointer, single-draw calls): predict_in_batches / viGP chunk loops call the
+    // posterior repeatedly with the same training set and theta; the reference re-inverts k_XX every time
+    // (gp.py:319-322 -> gp.py:269-271), here the factor L and its inverted diagonal blocks are kept.
+    struct {
+        bool valid = false;
+        int kind = -1, d = 0;
+        int64_t N = 0;
+        double jitter = 0.0;
+        std::vector<double> theta, X;
+        int info = 0;
+    } fcache;
+    int64_t cache_hits = 0;
 };
 
 }  // namespace
@@ -172,6 +185,10 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
         ctx->n_streams = (int)value;
         return B2GP_OK;
     }
+    if (strcmp(key, "drop_factor_cache") == 0) {
+        extra_of(ctx)->fcache.valid = false;
+        return B2GP_OK;
+    }
     return set_err(ctx, B2GP_ERR_ARG, "b2gp_set_option", "unknown key", __FILE__, __LINE__);
 }
 
@@ -183,6 +200,8 @@ extern "C" int b2gp_device_info(b2gp_ctx* ctx, int* sm_count, int* cc_major, int
     if (mem_bytes) *mem_bytes = ctx->mem_bytes;
     return B2GP_OK;
 }
+
+extern "C" int64_t b2gp_debug_cache_hits(b2gp_ctx* ctx) { return ctx ? extra_of(ctx)->cache_hits : -1; }
 
 extern "C" int b2gp_last_timing(b2gp_ctx* ctx, b2gp_timing* out) {
     if (!ctx || !out) return B2GP_ERR_ARG;
@@ -514,6 +533,28 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     std::vector<StageEvents> sev;
     if (timing) sev.resize((size_t)S);
 
+    // factor reuse (see Extra::fcache): same kind / N / d / jitter / theta / training inputs as the previous
+    // single-draw host-pointer call -> skip the Gram build and the factorisation
+    bool reuse = false;
+    if (S == 1 && !dev) {
+        auto& fc = ex->fcache;
+        reuse = fc.valid && fc.kind == kind && fc.N == N && fc.d == d && fc.jitter == jitter &&
+                memcmp(fc.theta.data(), theta, (size_t)nth * 8) == 0 && memcmp(fc.X.data(), Xtr, (size_t)N * d * 8) == 0;
+        if (!reuse) {
+            fc.valid = true;
+            fc.kind = kind;
+            fc.N = N;
+            fc.d = d;
+            fc.jitter = jitter;
+            fc.theta.assign(theta, theta + nth);
+            fc.X.assign(Xtr, Xtr + (size_t)N * d);
+        } else {
+            ex->cache_hits++;
+        }
+    } else {
+        ex->fcache.valid = false;
+    }
+
     for (int64_t s = 0; s < S; ++s) {
         Slot& sl = ctx->slots[s % nslots];
         cudaStream_t st = sl.stream;
@@ -527,11 +568,16 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
             for (int e = 0; e < 6; ++e) sev[s].e[e] = ex->pool.get();
             CUDA_TRY(ctx, cudaEventRecord(sev[s].e[0], st));
         }
-        // k_XX = kernel(X_train, X_train, params, noise, jitter)  (gp.py:269) -- lower triangle only
-        RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXtr, N, d, th, 1.0, jitter, 1, 1, A, ldA));
-        if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
-        // factor instead of jnp.linalg.inv (gp.py:271)
-        RET_IF(potrf_rec(ctx, st, A, ldA, N, Linv, inf, 0));
+        if (!reuse) {
+            // k_XX = kernel(X_train, X_train, params, noise, jitter)  (gp.py:269) -- lower triangle only
+            RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXtr, N, d, th, 1.0, jitter, 1, 1, A, ldA));
+            if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
+            // factor instead of jnp.linalg.inv (gp.py:271)
+            RET_IF(potrf_rec(ctx, st, A, ldA, N, Linv, inf, 0));
+        } else {
+            if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
+            CUDA_TRY(ctx, cudaMemcpyAsync(inf, &ex->fcache.info, sizeof(int), cudaMemcpyHostToDevice, st));
+        }
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[2], st));
         // k_pX = kernel(X_new, X_train, params, jitter=0.0)  (gp.py:268); same-shape inputs add 0 there
         RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXtr, N, d, th, 0.0, 0.0, 0, 0, Vt, ldV));
@@ -603,6 +649,7 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     CUDA_TRY(ctx, cudaEventRecord(ev_d, st0));
     RET_IF(tm.end(st0, nullptr));
     for (int64_t s = 0; s < S; ++s) info[s] = hinfo[s] != 0 ? hinfo[s] : -hinfo[S + s];
+    if (S == 1 && !dev) ex->fcache.info = hinfo[0];
 
     b2gp_timing& t = ex->last;
     float ms = 0.f;
@@ -795,6 +842,7 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     const bool dev = dev_ptrs(flags);
     Slot& sl = ctx->slots[0];
     cudaStream_t st = sl.stream;
+    ex->fcache.valid = false;
     CallTimer tm(ctx);
     RET_IF(tm.begin(st));
     const int nth = d + 3;
@@ -861,6 +909,7 @@ extern "C" int b2gp_sparse_partial(b2gp_ctx* ctx, int kind, const double* Xu, in
     ARG_CHECK(ctx, Xu && Xtr && yres && theta && Kpart && cpart && info);
     ARG_CHECK(ctx, M >= 1 && N >= 1 && d >= 1 && d <= GRAM_MAX_D && ldk >= M);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    extra_of(ctx)->fcache.valid = false;
     Slot& sl = ctx->slots[0];
     cudaStream_t st = sl.stream;
     CallTimer tm(ctx);
@@ -890,6 +939,7 @@ extern "C" int b2gp_sparse_finish(b2gp_ctx* ctx, int kind, const double* Xu, int
     ARG_CHECK(ctx, !want_var || var);
     ARG_CHECK(ctx, !want_cov || cov);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    extra_of(ctx)->fcache.valid = false;
     Slot& sl = ctx->slots[0];
     cudaStream_t st = sl.stream;
     CallTimer tm(ctx);
@@ -981,6 +1031,89 @@ extern "C" int b2gp_copy2d(b2gp_ctx* ctx, double* dst, int64_t ldd, const double
         CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)ldd * 8, src, (size_t)lds * 8, (size_t)cols * 8, (size_t)rows,
                                         cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ fit side
+// value and gradient (w.r.t. log lengthscale[d], log k_scale, log noise, log period) of the exact-GP log marginal
+// likelihood -- see mll.cuh.  X[N,d], yres[N] host or device pointers (flags); theta is a HOST pointer (d+3);
+// value, grad[d+3] and the optional alpha[N] = K^{-1} yres are HOST outputs.
+extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d, const double* theta,
+                        double jitter, unsigned flags, double* value, double* grad, double* alpha_out, int* info) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, X && yres && theta && value && info);
+    ARG_CHECK(ctx, N >= 1 && d >= 1 && d <= MLL_MAX_D);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    ex->fcache.valid = false;
+    const bool dev = dev_ptrs(flags);
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const int nth = d + 3;
+    const double *dX, *dy, *dth;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], X, (size_t)N * d * 8, dev, &dX));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], yres, (size_t)N * 8, dev, &dy));
+    RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, false, &dth));
+    const int64_t ld = round_up(N, 8);
+    const int64_t tiles = ceil_div(N, MLL_TILE);
+    RET_IF(ensure(ctx, sl.A, (size_t)N * ld * 8));
+    RET_IF(ensure(ctx, sl.Linv, (size_t)linv_bytes(N)));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    RET_IF(ensure(ctx, sl.misc, (size_t)(3 * ld + 64 + tiles * tiles * nth) * 8));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 8, st));
+    double* A = (double*)sl.A.p;
+    double* Linv = (double*)sl.Linv.p;
+    double* w = (double*)sl.misc.p;      // L^{-1} y
+    double* alpha = w + ld;              // K^{-1} y
+    double* sc = alpha + ld;             // [0] sum log L_ii, [1] |w|^2, [8..8+nth) grad
+    double* partial = sc + 64;
+    RET_IF(launch_gram(ctx, st, kind, dX, N, dX, N, d, dth, 1.0, jitter, 1, 1, A, ld));
+    RET_IF(potrf_rec(ctx, st, A, ld, N, Linv, dinfo, 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(w, dy, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+    RET_IF(trsm_rec(ctx, st, w, ld, 1, A, ld, N, Linv));
+    logdiag_kernel<<<1, 256, 0, st>>>(A, ld, N, sc);
+    rowdot2_kernel<<<1, RD_THREADS, 0, st>>>(w, ld, N, nullptr, 1.0, nullptr, sc + 1);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    if (grad || alpha_out) {
+        RET_IF(ensure(ctx, sl.cov, (size_t)N * ld * 8));
+        double* Bt = (double*)sl.cov.p;  // (L^{-1})^T
+        set_identity_kernel<<<grid_for(N * N), 256, 0, st>>>(Bt, ld, N);
+        CUDA_TRY(ctx, cudaGetLastError());
+        RET_IF(trsm_rec(ctx, st, Bt, ld, N, A, ld, N, Linv));
+        // alpha = L^{-T} w : alpha_i = <Bt[i,:], w>
+        rowdot2_kernel<<<(unsigned)N, RD_THREADS, 0, st>>>(Bt, ld, N, w, 1.0, alpha, nullptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 2;
+        if (grad) {
+            RET_IF(ensure(ctx, sl.Vt, (size_t)N * ld * 8));
+            double* Kinv = (double*)sl.Vt.p;
+            RET_IF(gemm_nt(ctx, st, N, N, N, 1.0, Bt, ld, Bt, ld, 0.0, Kinv, ld, true));
+            dim3 g((unsigned)tiles, (unsigned)tiles);
+            mll_grad_kernel<<<g, MLL_THREADS, 0, st>>>(dX, N, d, kind, dth, alpha, Kinv, ld, partial);
+            mll_finish_kernel<<<1, 32, 0, st>>>(partial, tiles * tiles, nth, sc + 8);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches += 2;
+        }
+    }
+    double hsc[8 + MLL_MAX_D + 3];
+    CUDA_TRY(ctx, cudaMemcpyAsync(hsc, sc, sizeof hsc, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (alpha_out) CUDA_TRY(ctx, cudaMemcpyAsync(alpha_out, alpha, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    *value = -0.5 * hsc[1] - hsc[0] - 0.5 * (double)N * 1.8378770664093453;  // log(2 pi)
+    if (grad)
+        for (int k = 0; k < nth; ++k) grad[k] = hsc[8 + k];
+    if (*info != 0) {
+        *value = NAN;
+        if (grad)
+            for (int k = 0; k < nth; ++k) grad[k] = NAN;
+    }
+    ex->last.flops = (double)N * N * N * (grad ? 1.0 / 3 + 1.0 + 1.0 : 1.0 / 3);
     return B2GP_OK;
 }
 

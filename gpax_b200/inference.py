@@ -1,23 +1,273 @@
 """
-inference.py -- hyper-parameter inference for `.fit()` (the row after the
-posterior path).  Placeholder until the marginal-likelihood value+gradient kernel lands.
+inference.py -- hyper-parameter inference behind `.fit()`.
+
+The reference hands `ExactGP.model` (gpax/models/gp.py:137-164) to NumPyro: NUTS/MCMC for ExactGP.fit
+(gp.py:207-218) and SVI with Adam(b1=0.5) and an AutoDelta / AutoNormal guide for viGP.fit (vigp.py:108-120).
+Here the model's log joint is evaluated directly: the likelihood term and its gradient come from the GPU
+(b2gp_mll: Cholesky + solves + fused gradient reduction), the priors are the LogNormal(0,1) defaults of
+gp.py:222-247 (or gpax_b200.priors objects), and the samplers / optimiser are small host-side NumPy loops.
+Custom `kernel_prior` / `noise_prior` *functions* are NumPyro programs and cannot be interpreted here.
 """
+import math
+
+import numpy as np
+
+from . import priors as P
+from .utils import seed_from_key
 
 
-def _todo(name):
-    raise NotImplementedError(
-        f"{name}: the fit path (NUTS / SVI over the marginal likelihood, gpax/models/gp.py:166-220, "
-        "vigp.py:77-123) is the next row of the scope table; pass `samples=` / `params` to the predict "
-        "path, which is what this build accelerates.")
+class LogJoint:
+    """log p(y, theta) over the unconstrained vector u, with gradient; theta = (k_length[d], k_scale, noise[, period])."""
+
+    def __init__(self, model, jitter=1e-6):
+        if model._fused is None:
+            raise NotImplementedError("fit() needs kernel 'RBF', 'Matern' or 'Periodic'")
+        if model.kernel_prior is not None or model.noise_prior is not None:
+            raise NotImplementedError("kernel_prior / noise_prior are NumPyro programs; use lengthscale_prior_dist / "
+                                      "noise_prior_dist with gpax_b200.priors objects")
+        if model.mean_fn is not None and model.mean_fn_prior is not None:
+            raise NotImplementedError("fit() with a probabilistic mean function is not implemented")
+        self.m, self.jitter = model, float(jitter)
+        X, y = model._train_arrays()
+        self.X, self.d = X, X.shape[1]
+        self.y = y if model.mean_fn is None else y - np.asarray(model.mean_fn(X), dtype=np.float64).squeeze()
+        self.kind = model._fused
+        d = self.d
+        lp = model.lengthscale_prior_dist or P.LogNormal(0.0, 1.0)       # gp.py:235-239
+        npd = model.noise_prior_dist or P.LogNormal(0.0, 1.0)            # gp.py:222-227
+        self.names = ["k_length"] * d + ["k_scale", "noise"]
+        self.priors = [lp] * d + [P.LogNormal(0.0, 1.0), npd]            # gp.py:240
+        self.idx = list(range(d + 2))                                     # position in the (d+3) theta vector
+        if self.kind == "Periodic":                                       # gp.py:241-244
+            self.names.append("period")
+            self.priors.append(P.LogNormal(0.0, 1.0))
+            self.idx.append(d + 2)
+        for pr in self.priors:
+            if not isinstance(pr, P.Prior):
+                raise TypeError("priors must be gpax_b200.priors objects (numpyro distributions cannot be used here)")
+        self.dim = len(self.priors)
+        self.n_evals = 0
+
+    def theta_of(self, u):
+        th = np.ones(self.d + 3)
+        for k, (pr, i) in enumerate(zip(self.priors, self.idx)):
+            th[i] = pr.transform(u[k])
+        return th
+
+    def init_u(self):
+        """init_to_median: the reference's NUTS uses init_to_median(num_samples=10) (gp.py:208); exact medians here"""
+        return np.array([float(pr.inverse(pr.median())) for pr in self.priors])
+
+    def __call__(self, u, jacobian):
+        """log p(y | theta(u)) + sum log p(theta_k) [+ log |dtheta/du| if jacobian]; returns (value, grad_u)"""
+        th = self.theta_of(u)
+        val, g, _, info = self.m.ctx.mll(self.kind, self.X, self.y, th, self.jitter, want_grad=True)
+        self.n_evals += 1
+        if info != 0 or not np.isfinite(val):
+            return -np.inf, np.zeros(self.dim)
+        grad = np.zeros(self.dim)
+        for k, (pr, i) in enumerate(zip(self.priors, self.idx)):
+            t = th[i]
+            dt = float(pr.dtheta_du(u[k]))
+            val += float(pr.log_prob(t))
+            grad[k] = g[i] / t * dt + float(pr.dlog_prob(t)) * dt       # g is d/dlog(theta)
+            if jacobian:
+                val += float(pr.log_abs_jac(u[k]))
+                grad[k] += float(pr.dlog_abs_jac(u[k]))
+        return val, grad
+
+    def to_dict(self, U):
+        """rows of unconstrained vectors -> dict of constrained samples with the reference's site names / shapes"""
+        U = np.atleast_2d(U)
+        th = np.stack([self.theta_of(u) for u in U])
+        out = {"k_length": th[:, :self.d], "k_scale": th[:, self.d], "noise": th[:, self.d + 1]}
+        if self.kind == "Periodic":
+            out["period"] = th[:, self.d + 2]
+        return out
 
 
-def fit_exact_gp(model, rng_key, num_warmup, num_samples, num_chains, progress_bar, **kwargs):
-    _todo("ExactGP.fit")
+# ---------------------------------------------------------------------------------------------- SVI
+class SVIState:
+    def __init__(self, losses, guide, loc, scale):
+        self.losses, self.guide, self.loc, self.scale = losses, guide, loc, scale
 
 
 def fit_vi_gp(model, rng_key, num_steps, step_size, progress_bar, **kwargs):
-    _todo("viGP.fit")
+    """vigp.py:108-120: Adam(step_size, b1=0.5), AutoDelta (MAP in the constrained space, no Jacobian) or AutoNormal
+    (mean-field normal over u, init scale 0.1, one reparameterised draw per step).  Returns (state, median dict)."""
+    lj = LogJoint(model, kwargs.get("jitter", 1e-6))
+    rng = seed_from_key(rng_key)
+    normal = model.guide_type == "normal"
+    loc = lj.init_u()
+    rho = np.full(lj.dim, math.log(0.1))            # log sigma
+    params = np.concatenate([loc, rho]) if normal else loc.copy()
+    m1, m2 = np.zeros_like(params), np.zeros_like(params)
+    b1, b2, eps = 0.5, 0.999, 1e-8
+    losses = []
+    for t in range(1, int(num_steps) + 1):
+        if normal:
+            mu, r = params[:lj.dim], params[lj.dim:]
+            e = rng.standard_normal(lj.dim)
+            val, g = lj(mu + np.exp(r) * e, jacobian=True)
+            elbo = val + r.sum() + 0.5 * lj.dim * (1 + math.log(2 * math.pi))
+            grad = np.concatenate([g, g * e * np.exp(r) + 1.0])
+        else:
+            elbo, grad = lj(params, jacobian=False)
+        losses.append(-elbo)
+        if not np.isfinite(elbo):
+            grad = np.zeros_like(params)
+        m1 = b1 * m1 + (1 - b1) * (-grad)
+        m2 = b2 * m2 + (1 - b2) * grad * grad
+        params = params - step_size * (m1 / (1 - b1 ** t)) / (np.sqrt(m2 / (1 - b2 ** t)) + eps)
+        if progress_bar and (t % max(1, num_steps // 10) == 0 or t == num_steps):
+            print(f"svi step {t}/{num_steps}  loss {losses[-1]:.4f}")
+    loc = params[:lj.dim]
+    med = {k: (v[0] if v.ndim == 1 else v[0]) for k, v in lj.to_dict(loc).items()}   # guide median (vigp.py:125-127)
+    return SVIState(np.array(losses), "normal" if normal else "delta", loc, np.exp(params[lj.dim:]) if normal else None), med
 
 
 def fit_sparse_gp(model, rng_key, Xu0, num_steps, step_size, progress_bar, **kwargs):
-    _todo("viSparseGP.fit")
+    raise NotImplementedError(
+        "viSparseGP.fit (VFE ELBO with learnable inducing points, gpax/models/sparse_gp.py:62-171) is not built yet: "
+        "set m.X_train, m.y_train, m.Xu and pass params to predict / get_mvn_posterior")
+
+
+# ---------------------------------------------------------------------------------------------- NUTS
+class MCMCResult:
+    """What ExactGP needs from numpyro's MCMC object: get_samples(group_by_chain)."""
+
+    def __init__(self, samples_by_chain, stats):
+        self._s, self.stats = samples_by_chain, stats
+
+    def get_samples(self, group_by_chain=False):
+        if group_by_chain:
+            return self._s
+        return {k: v.reshape((-1,) + v.shape[2:]) for k, v in self._s.items()}
+
+
+def _leapfrog(lj, u, r, g, eps, minv):
+    r = r + 0.5 * eps * g
+    u = u + eps * minv * r
+    lp, g = lj(u, jacobian=True)
+    r = r + 0.5 * eps * g
+    return u, r, lp, g
+
+
+def _find_eps(lj, u, lp, g, rng, minv):
+    eps = 1.0
+    r = rng.standard_normal(u.size) / np.sqrt(minv)
+    h0 = lp - 0.5 * np.dot(r, minv * r)
+    _, r1, lp1, _ = _leapfrog(lj, u, r, g, eps, minv)
+    h1 = lp1 - 0.5 * np.dot(r1, minv * r1)
+    a = 1.0 if (np.isfinite(h1) and h1 - h0 > math.log(0.5)) else -1.0
+    for _ in range(50):
+        if not (np.isfinite(h1) and a * (h1 - h0) > -a * math.log(2)):
+            if np.isfinite(h1) or a < 0:
+                break
+        eps *= 2.0 ** a
+        _, r1, lp1, _ = _leapfrog(lj, u, r, g, eps, minv)
+        h1 = lp1 - 0.5 * np.dot(r1, minv * r1)
+    return eps
+
+
+def _nuts_draw(lj, u0, lp0, g0, eps, rng, minv, max_depth=10):
+    """one transition of the no-U-turn sampler with multinomial sampling along the trajectory"""
+    r0 = rng.standard_normal(u0.size) / np.sqrt(minv)
+    h0 = lp0 - 0.5 * np.dot(r0, minv * r0)
+    um, rm, gm = u0.copy(), r0.copy(), g0.copy()
+    up, rp, gp = u0.copy(), r0.copy(), g0.copy()
+    u, lp, g = u0.copy(), lp0, g0.copy()
+    logw = 0.0           # log of the total weight of the current tree (relative to h0)
+    depth, alpha_sum, n_alpha, diverged = 0, 0.0, 0, False
+
+    def build(u_, r_, g_, v, j):
+        nonlocal alpha_sum, n_alpha, diverged
+        if j == 0:
+            u1, r1, lp1, g1 = _leapfrog(lj, u_, r_, g_, v * eps, minv)
+            h1 = lp1 - 0.5 * np.dot(r1, minv * r1) if np.isfinite(lp1) else -np.inf
+            dh = h1 - h0
+            if not np.isfinite(dh):
+                dh = -np.inf
+            alpha_sum += min(1.0, math.exp(min(dh, 0.0))) if dh > -np.inf else 0.0
+            n_alpha += 1
+            ok = dh > -1000.0
+            if not ok:
+                diverged = True
+            return u1, r1, g1, u1, r1, g1, u1, lp1, g1, dh, ok
+        a = build(u_, r_, g_, v, j - 1)
+        um_, rm_, gm_, up_, rp_, gp_, uc, lpc, gc, lw, ok = a
+        if not ok:
+            return a
+        if v == -1:
+            b = build(um_, rm_, gm_, v, j - 1)
+            um_, rm_, gm_ = b[0], b[1], b[2]
+        else:
+            b = build(up_, rp_, gp_, v, j - 1)
+            up_, rp_, gp_ = b[3], b[4], b[5]
+        lw2, ok2 = b[9], b[10]
+        lw_tot = np.logaddexp(lw, lw2)
+        if ok2 and math.log(rng.uniform()) < lw2 - lw_tot:
+            uc, lpc, gc = b[6], b[7], b[8]
+        span = up_ - um_
+        ok = ok2 and np.dot(span, rm_) >= 0 and np.dot(span, rp_) >= 0
+        return um_, rm_, gm_, up_, rp_, gp_, uc, lpc, gc, lw_tot, ok
+
+    while depth < max_depth:
+        v = 1 if rng.uniform() < 0.5 else -1
+        if v == -1:
+            t = build(um, rm, gm, v, depth)
+            um, rm, gm = t[0], t[1], t[2]
+        else:
+            t = build(up, rp, gp, v, depth)
+            up, rp, gp = t[3], t[4], t[5]
+        lw2, ok = t[9], t[10]
+        if ok and math.log(rng.uniform()) < lw2 - logw:      # biased progressive sampling
+            u, lp, g = t[6], t[7], t[8]
+        logw = np.logaddexp(logw, lw2)
+        span = up - um
+        if not ok or np.dot(span, rm) < 0 or np.dot(span, rp) < 0:
+            break
+        depth += 1
+    return u, lp, g, alpha_sum / max(n_alpha, 1), depth, diverged
+
+
+def fit_exact_gp(model, rng_key, num_warmup, num_samples, num_chains, progress_bar, **kwargs):
+    """gp.py:207-218: NUTS with dual-averaging step-size adaptation (target accept 0.8) and a diagonal mass matrix
+    estimated over the second half of warm-up; chains run one after another ('sequential')."""
+    lj = LogJoint(model, kwargs.get("jitter", 1e-6))
+    root = seed_from_key(rng_key)
+    chains, stats = [], []
+    for c in range(int(num_chains)):
+        rng = np.random.default_rng(root.integers(0, 2 ** 63))
+        u = lj.init_u() + (0.0 if c == 0 else 0.1 * rng.standard_normal(lj.dim))
+        lp, g = lj(u, jacobian=True)
+        minv = np.ones(lj.dim)
+        eps = _find_eps(lj, u, lp, g, rng, minv)
+        mu, hbar, log_eps_bar, gamma, t0, kappa, delta = math.log(10 * eps), 0.0, 0.0, 0.05, 10.0, 0.75, 0.8
+        draws, warm_buf, div = [], [], 0
+        for it in range(int(num_warmup) + int(num_samples)):
+            u, lp, g, acc, depth, dv = _nuts_draw(lj, u, lp, g, eps, rng, minv)
+            if it < num_warmup:
+                m = it + 1
+                hbar = (1 - 1 / (m + t0)) * hbar + (delta - acc) / (m + t0)
+                log_eps = mu - math.sqrt(m) / gamma * hbar
+                eta = m ** (-kappa)
+                log_eps_bar = eta * log_eps + (1 - eta) * log_eps_bar
+                eps = math.exp(log_eps)
+                if it >= num_warmup // 2:
+                    warm_buf.append(u.copy())
+                if it == num_warmup - 1:
+                    if len(warm_buf) >= 20:
+                        var = np.var(np.array(warm_buf), axis=0)
+                        minv = (len(warm_buf) * var + 1e-3 * 5) / (len(warm_buf) + 5)    # regularised, as Stan
+                    eps = math.exp(log_eps_bar)
+            else:
+                draws.append(u.copy())
+                div += int(dv)
+            if progress_bar and (it + 1) % max(1, (num_warmup + num_samples) // 10) == 0:
+                print(f"chain {c} iter {it + 1}/{num_warmup + num_samples} step {eps:.3g} depth {depth} lp {lp:.3f}")
+        chains.append(np.array(draws))
+        stats.append({"step_size": eps, "divergences": div, "grad_evals": lj.n_evals})
+    per_chain = [lj.to_dict(ch) for ch in chains]
+    by_chain = {k: np.stack([pc[k] for pc in per_chain]) for k in per_chain[0]}
+    return MCMCResult(by_chain, stats)

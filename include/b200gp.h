@@ -158,6 +158,16 @@ int  b2gp_sparse_posterior(b2gp_ctx* ctx, int kind,
                            double* mean, double* var, double* cov,
                            int* info, b2gp_timing* timing);
 
+/* Fit side: value and gradient of the exact-GP log marginal likelihood
+ *   log N(yres; 0, K_theta),  K_theta = kernel(X, X, theta, noise, jitter)
+ * i.e. the numpyro.sample("y", MultivariateNormal(f_loc, covariance_matrix=k), obs=y) term of
+ * gpax/models/gp.py:158-164 and its reverse-mode derivative.  grad[d+3] is w.r.t. (log lengthscale[0..d),
+ * log k_scale, log noise, log period); theta (d+3) is a HOST pointer; value, grad, alpha_out[N] = K^{-1} yres
+ * (optional) are HOST outputs; X, yres follow `flags`.  d <= 16.                                          */
+int  b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d,
+              const double* theta, double jitter, unsigned flags,
+              double* value, double* grad, double* alpha_out, int* info);
+
 /* ---- multi-GPU building blocks.  One process per GPU; the exchange steps
  * (panel broadcast, M x M all-reduce) are issued by the host side over NCCL on these same device
  * buffers (gpax_b200/distributed.py).  All array pointers below are DEVICE pointers. ----------------*/
