@@ -14,7 +14,7 @@ Gram(k_XX) -> N x N Cholesky -> Gram(k_pX) -> triangular solves -> posterior mea
   value   posteriors/s with X, y, X_new, theta resident in HBM (device-pointer C-ABI call)
   e2e     the same through the host-buffer C-ABI call (pinned host memory in, host memory out:
           H2D of X, y, X_new, theta and D2H of mean, var, info inside the timed region)
-  roofline  dominant kernel = the DMMA trailing-update GEMM/SYRK (gemm_nt_kernel): algorithmic flops of
+  roofline  dominant kernel = the DMMA trailing-update GEMM/SYRK (gemm_tma_kernel): algorithmic flops of
           the top-level SYRK of the N=16384 factorisation (8192 x 8192, k = 8192, lower half) / its
           CUDA-event duration, against the fp64 GEMM peak measured live with cuBLAS (torch.matmul fp64;
           MEASURED_PEAKS.json carries no fp64 figure)
@@ -356,7 +356,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
-                     "traffic": traffic, "kernel": "gemm_nt_kernel<128,128> (DMMA.8x8x4 SYRK, 8192x8192 k=8192 lower)",
+                     "traffic": traffic, "kernel": "gemm_tma_kernel<3,2> (persistent, TMA + mbarrier ring, DMMA.8x8x4; SYRK 8192x8192 k=8192 lower) + 64x64 tail launch",
                      "flops_per_launch": dom["flops_per_launch"], "ms_per_launch": dom["ms"], "peak_source": peak_src},
     }
     if not args.no_cpu_baseline:

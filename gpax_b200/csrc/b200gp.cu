@@ -4,6 +4,7 @@
 // produced by the sm_100a kernels in gram.cuh / gemm_dmma.cuh / potrf.cuh / posterior.cuh.
 #include "common.cuh"
 #include "gemm_dmma.cuh"
+#include "gemm_tma.cuh"
 #include "gram.cuh"
 #include "mll.cuh"
 #include "posterior.cuh"
@@ -183,6 +184,10 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     if (strcmp(key, "streams") == 0) {
         ARG_CHECK(ctx, value >= 1 && value <= B2GP_MAX_STREAMS);
         ctx->n_streams = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "tma") == 0) {
+        ctx->use_tma = value ? 1 : 0;
         return B2GP_OK;
     }
     if (strcmp(key, "drop_factor_cache") == 0) {
@@ -1137,5 +1142,34 @@ extern "C" int b2gp_debug_leaf(b2gp_ctx* ctx, int n, double* A_dev, int64_t lda,
     CUDA_TRY(ctx, cudaGetLastError());
     CUDA_TRY(ctx, cudaMemcpyAsync(prof_host, dprof, 64 * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    return B2GP_OK;
+}
+
+// Development aid: time one GEMM/SYRK launch with an explicit tile configuration (device pointers).
+extern "C" int b2gp_debug_gemm_cfg(b2gp_ctx* ctx, int cfg, int64_t m, int64_t n, int64_t k, const double* A, int64_t lda,
+                                   const double* B, int64_t ldb, double* C, int64_t ldc, int lower, double* ms_out) {
+    if (!ctx) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    GemmArgs a;
+    a.m = (int)m; a.n = (int)n; a.k = (int)k; a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.C = C; a.ldc = ldc;
+    a.alpha = -1.0; a.beta = 1.0; a.lower_only = lower;
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
+    int rc = B2GP_ERR_ARG;
+    switch (cfg) {
+        case 0: rc = launch_gemm_cfg<128, 128, 2, 4, 4, 1>(ctx, st, a); break;
+        case 1: rc = launch_gemm_cfg<128, 128, 4, 4, 4, 1>(ctx, st, a); break;
+        case 2: rc = launch_gemm_cfg<128, 128, 2, 4, 3, 1>(ctx, st, a); break;
+        case 3: rc = launch_gemm_cfg<128, 128, 4, 2, 4, 1>(ctx, st, a); break;
+        case 4: rc = launch_gemm_cfg<128, 128, 2, 8, 4, 1>(ctx, st, a); break;
+        case 5: rc = launch_gemm_cfg<128, 128, 4, 4, 3, 1>(ctx, st, a); break;
+        default: break;
+    }
+    RET_IF(rc);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_b));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    *ms_out = ms;
     return B2GP_OK;
 }

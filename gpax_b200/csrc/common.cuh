@@ -36,6 +36,7 @@ struct b2gp_ctx {
     int cc_major = 0, cc_minor = 0;
     size_t mem_bytes = 0;
     int n_streams = 2;
+    int use_tma = 1;  // large GEMMs through the TMA / mbarrier persistent kernel (gemm_tma.cuh)
     Slot slots[B2GP_MAX_STREAMS];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
     // staging for host-pointer entry points

@@ -30,6 +30,8 @@ struct GemmArgs {
     double alpha, beta;
     int lower_only;
     int tiles_m, tiles_n;
+    int tile_base = 0;  // first 128x128 tile index covered by this launch (tail launches, see gemm_tma.cuh)
+    int sub = 0;        // 1: blockIdx.x enumerates the four 64x64 quarters of 128x128 tiles tile_base, tile_base+1, ...
 };
 
 constexpr int GEMM_BK = 16;
@@ -89,16 +91,24 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB) gemm_nt_kernel(co
     extern __shared__ __align__(16) double smem[];
 
     int ti, tj;
-    if (p.lower_only) {
-        const int x = blockIdx.x;
-        int t = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
-        while ((int64_t)(t + 1) * (t + 2) / 2 <= x) ++t;
-        while ((int64_t)t * (t + 1) / 2 > x) --t;
-        ti = t;
-        tj = x - t * (t + 1) / 2;
-    } else {
-        ti = blockIdx.x / p.tiles_n;
-        tj = blockIdx.x % p.tiles_n;
+    {
+        const int x = p.sub ? p.tile_base + (int)(blockIdx.x >> 2) : p.tile_base + (int)blockIdx.x;
+        const int tn = p.sub ? (p.tiles_n + 1) / 2 : p.tiles_n;   // tile columns in units of the indexed (128-wide) tiles
+        if (p.lower_only) {
+            int t = (int)((sqrt(8.0 * (double)x + 1.0) - 1.0) * 0.5);
+            while ((int64_t)(t + 1) * (t + 2) / 2 <= x) ++t;
+            while ((int64_t)t * (t + 1) / 2 > x) --t;
+            ti = t;
+            tj = x - t * (t + 1) / 2;
+        } else {
+            ti = x / tn;
+            tj = x % tn;
+        }
+        if (p.sub) {
+            ti = 2 * ti + (int)((blockIdx.x >> 1) & 1);
+            tj = 2 * tj + (int)(blockIdx.x & 1);
+            if (p.lower_only && tj > ti) return;
+        }
     }
     const int row0 = ti * BM, col0 = tj * BN;
     const int tid = threadIdx.x;
@@ -211,6 +221,8 @@ static int launch_gemm_cfg(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     return B2GP_OK;
 }
 
+static int gemm_tma_dispatch(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a);  // gemm_tma.cuh
+
 // C = beta*C + alpha*A*B^T.  lower_only requires a square C (m == n) whose diagonal is the matrix
 // diagonal.  `inplace_rows` marks the B <- B*Linv^T use where C aliases A: that is only safe with a
 // single column tile (n <= 128), which the 128-wide configuration guarantees.
@@ -237,7 +249,15 @@ static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t
     // use (C aliases A, n <= 128) needs a single column tile, which all three configurations give.
     const int64_t tm128 = ceil_div(m, 128), tn128 = ceil_div(n, 128);
     const int64_t t128 = lower_only ? tm128 * (tm128 + 1) / 2 : tm128 * tn128;
-    if (t128 >= 112) return launch_gemm_cfg<128, 128, 2, 4, 4, 1>(ctx, st, a);
+    if (t128 >= 112) {
+        if (ctx->use_tma) {
+            const int rc = gemm_tma_dispatch(ctx, st, a);
+            if (rc != B2GP_ERR_UNSUPPORTED) return rc;
+        }
+        // measured (tools/gemm_cfg.py): 3 stages beat 4 at large k; 16 warps (4 per SM sub-partition) beat 8 at small k
+        if (k <= 1024) return launch_gemm_cfg<128, 128, 4, 4, 3, 1>(ctx, st, a);
+        return launch_gemm_cfg<128, 128, 2, 4, 3, 1>(ctx, st, a);
+    }
     if (lower_only) {
         // square tiles only for the triangular tile map
         return launch_gemm_cfg<64, 64, 2, 4, 4, 2>(ctx, st, a);

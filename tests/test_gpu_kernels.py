@@ -95,8 +95,31 @@ def test_syrk_lower(ctx, n, k):
     np.testing.assert_array_equal(np.triu(C, 1), np.triu(C0, 1))               # strict upper untouched
 
 
+@pytest.mark.parametrize("m,n,k,lower", [(2048, 2048, 300, False), (1700, 2333, 77, False), (2100, 2100, 257, True),
+                                           (4096, 4096, 1024, True)])
+def test_gemm_large_tma_path(ctx, m, n, k, lower):
+    """>= 112 tiles of 128x128: the persistent TMA / mbarrier kernel (gemm_tma.cuh), ragged edges zero-filled by TMA;
+    and the same call with the TMA path switched off must give the same bits (same DMMA accumulation order)"""
+    rng = np.random.default_rng(m + k)
+    A = rng.standard_normal((m, k))
+    B = A if lower else rng.standard_normal((n, k))
+    C0 = rng.standard_normal((m, n))
+    C = ctx.gemm_nt(A, B, C0, alpha=-1.0, beta=1.0, lower_only=lower)
+    ref = C0 - A @ B.T
+    tol = 1e-13 * k ** 0.5 * np.abs(ref).max()
+    if lower:
+        np.testing.assert_allclose(np.tril(C), np.tril(ref), rtol=0, atol=tol)
+        np.testing.assert_array_equal(np.triu(C, 1), np.triu(C0, 1))
+    else:
+        np.testing.assert_allclose(C, ref, rtol=0, atol=tol)
+    ctx.set_option("tma", 0)
+    C2 = ctx.gemm_nt(A, B, C0, alpha=-1.0, beta=1.0, lower_only=lower)
+    ctx.set_option("tma", 1)
+    np.testing.assert_array_equal(C, C2)
+
+
 # ------------------------------------------------------------------ Cholesky + triangular solve
-@pytest.mark.parametrize("n", [1, 2, 31, 64, 65, 127, 128, 129, 200, 256, 300, 511, 777, 1024, 1500])
+@pytest.mark.parametrize("n", [1, 2, 31, 64, 65, 127, 128, 129, 200, 256, 300, 511, 777, 1024, 1500, 4100])
 def test_potrf(ctx, n):
     rng = np.random.default_rng(n)
     A = spd(rng, n)
