@@ -170,33 +170,63 @@ class BlockCyclicGP:
             w = self.width(j)
             self.ops.gram(kind, X[j * self.nb:], X[j * self.nb: j * self.nb + w], theta, diag, True, self.col[j][:, :w])
 
-    # ---- right-looking factorisation, panel broadcast per block column
+    # ---- right-looking factorisation with look-ahead: while the ranks apply panel k to the block columns they
+    #      own, the owner of column k+1 has already brought that column up to date, factored it, and its panel
+    #      is travelling (asynchronous NCCL broadcast into the second panel buffer)
+    def _panel(self, k, info):
+        """owner only: factor the diagonal block of column k and solve the rows below it"""
+        w, rows = self.width(k), self.N - k * self.nb
+        panel = self.col[k]
+        i = self.ops.potrf_inv(panel[:w, :w], self.linv[k])
+        if i and not info[0]:
+            info[0] = k * self.nb + i
+        if rows > w:
+            self.ops.trsm_inv(panel[:w, :w], self.linv[k], panel[w:, :w])
+
+    def _update(self, panel, k, j):
+        """col[j] -= panel[rows of j] * panel[block j]^T with panel = L[k*nb:, block k]"""
+        off, wj, w = (j - k) * self.nb, self.width(j), self.width(k)
+        self.ops.gemm_nt(panel[off:, :w], panel[off: off + wj, :w], self.col[j][:, :wj], -1.0, 1.0)
+
+    def _bcast(self, k, buf, async_op):
+        """broadcast panel k from its owner; returns (view of the panel on this rank, work handle or None)"""
+        rows, own = self.N - k * self.nb, self.owner(k)
+        panel = self.col[k] if self.rank == own else buf[:rows]
+        work = None
+        if self.world > 1:
+            self._sync()
+            src = self.dist.get_global_rank(self.group, own) if self.group else own
+            work = self.dist.broadcast(panel, src=src, group=self.group, async_op=async_op)
+            self.bytes_broadcast += panel.numel() * 8
+            if not async_op:
+                self._sync()
+                work = None
+        return panel, work
+
     def factor(self):
-        ops, nb, N = self.ops, self.nb, self.N
-        info = 0
+        info = [0]
+        if not hasattr(self, "pbuf2"):
+            self.pbuf2 = self.ops.empty((self.N, self.nb)) if self.world > 1 else self.pbuf
+        cur, nxt = self.pbuf, self.pbuf2
+        if self.rank == self.owner(0):
+            self._panel(0, info)
+        panel, _ = self._bcast(0, cur, False)
         for k in range(self.nblk):
-            w, rows, own = self.width(k), N - k * nb, self.owner(k)
-            if self.rank == own:
-                panel = self.col[k]
-                i = ops.potrf_inv(panel[:w, :w], self.linv[k])
-                if i and not info:
-                    info = k * nb + i
-                if rows > w:
-                    ops.trsm_inv(panel[:w, :w], self.linv[k], panel[w:, :w])
-            else:
-                panel = self.pbuf[:rows]
-            if self.world > 1:
-                self._sync()
-                self.dist.broadcast(panel, src=self.dist.get_global_rank(self.group, own) if self.group else own,
-                                    group=self.group)
-                self._sync()
-                self.bytes_broadcast += panel.numel() * 8
+            nxt_panel, work = None, None
+            if k + 1 < self.nblk:
+                if self.rank == self.owner(k + 1):
+                    self._update(panel, k, k + 1)          # look-ahead column first ...
+                    self._panel(k + 1, info)               # ... factor it ...
+                nxt_panel, work = self._bcast(k + 1, nxt, True)   # ... and send it while the rest is updated
             for j in self.owned:
-                if j <= k:
-                    continue
-                off, wj = (j - k) * nb, self.width(j)
-                ops.gemm_nt(panel[off:, :w], panel[off: off + wj, :w], self.col[j][:, :wj], -1.0, 1.0)
-        self.info = self._max_int(info)
+                if j > k + 1:
+                    self._update(panel, k, j)
+            if work is not None:
+                work.wait()
+                self._sync()
+            panel = nxt_panel
+            cur, nxt = nxt, cur
+        self.info = self._max_int(info[0])
         return self.info
 
     def _max_int(self, v):
