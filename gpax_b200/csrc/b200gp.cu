@@ -357,12 +357,9 @@ extern "C" int b2gp_potrf(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, int*
     RET_IF(potrf_rec(ctx, st, dA, ld, n, (double*)ctx->last_linv.p, (int*)ctx->d_info.p, 0));
     ctx->last_n = n;
     if (!dev) {
-        // copy back only the lower triangle's rows; the strict upper triangle of the caller's array is
-        // preserved by copying row i's first i+1 entries
-        // (one 2-D copy of the full rows followed by a host-side restore would touch the upper part)
-        std::vector<double> tmp;  // not used: rows are copied individually below for n small, else via 2-D copy + fixup
-        // Simple and exact: stage the whole factor on the host in a temporary, then write j <= i.
-        tmp.resize((size_t)n * n);
+        // the strict upper triangle of the caller's array is documented as untouched: stage the factor on the
+        // host and write back j <= i only
+        std::vector<double> tmp((size_t)n * n);
         CUDA_TRY(ctx, cudaMemcpy2DAsync(tmp.data(), (size_t)n * 8, dA, (size_t)ld * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(ctx, cudaStreamSynchronize(st));
         for (int64_t i = 0; i < n; ++i) memcpy(A + i * lda, tmp.data() + i * n, (size_t)(i + 1) * 8);
