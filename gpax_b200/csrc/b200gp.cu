@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
+#include "ozaki.cuh"
 #include "gram.cuh"
 #include "mll.cuh"
 #include "posterior.cuh"
@@ -146,6 +147,12 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         free_buf(s.cov);
         free_buf(s.LinvC);
         free_buf(s.misc);
+        free_buf(s.oz.planesA);
+        free_buf(s.oz.planesB);
+        free_buf(s.oz.scaleA);
+        free_buf(s.oz.scaleB);
+        free_buf(s.oz.prof);
+        free_buf(s.oz.tiles);
         for (int e = 0; e < 8; ++e) cudaEventDestroy(s.ev[e]);
         cudaStreamDestroy(s.stream);
     }
@@ -162,6 +169,7 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         for (int i = 0; i < B2GP_MAX_STREAMS; ++i) cudaEventDestroy(ex->slot_done[i]);
         cudaEventDestroy(ex->inputs_ready);
         free_buf(ex->theta1);
+
         free_buf(ex->potrf_buf);
         for (auto& b : ex->gemm_buf) free_buf(b);
         for (void* p : ex->user_allocs) cudaFree(p);
@@ -184,6 +192,11 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     if (strcmp(key, "streams") == 0) {
         ARG_CHECK(ctx, value >= 1 && value <= B2GP_MAX_STREAMS);
         ctx->n_streams = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "ozaki") == 0) {
+        ARG_CHECK(ctx, value == 0 || value == 7 || value == 8);
+        ctx->ozaki = (int)value;
         return B2GP_OK;
     }
     if (strcmp(key, "tma") == 0) {
@@ -1168,5 +1181,37 @@ extern "C" int b2gp_debug_gemm_cfg(b2gp_ctx* ctx, int cfg, int64_t m, int64_t n,
     float ms = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
     *ms_out = ms;
+    return B2GP_OK;
+}
+
+// Development aid: C[m,n] += alpha * A B^T through the int8 tcgen05 path (ozaki.cuh), device pointers, S = 7 or 8 digit planes.
+extern "C" int b2gp_debug_ozaki(b2gp_ctx* ctx, int S, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                                const double* B, int64_t ldb, double* C, int64_t ldc, int lower, double* ms_out) {
+    if (!ctx) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    Extra* ex = extra_of(ctx);
+    RET_IF(ensure(ctx, ctx->slots[0].oz.prof, 148 * 4 * 8));
+    CUDA_TRY(ctx, cudaMemsetAsync(ctx->slots[0].oz.prof.p, 0, 148 * 4 * 8, st));
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
+    int rc;
+    if (S == 7)
+        rc = ozaki_gemm_nt<7>(ctx, st, ctx->slots[0].oz, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower != 0);
+    else
+        rc = ozaki_gemm_nt<8>(ctx, st, ctx->slots[0].oz, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower != 0);
+    RET_IF(rc);
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_b));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    if (ms_out) *ms_out = ms;
+    {
+        long long h[148 * 4];
+        CUDA_TRY(ctx, cudaMemcpy(h, ctx->slots[0].oz.prof.p, sizeof h, cudaMemcpyDeviceToHost));
+        double w = 0, e = 0, u = 0, t = 0;
+        for (int i = 0; i < 148; ++i) { w += h[4 * i]; e += h[4 * i + 1]; u += h[4 * i + 2]; t += h[4 * i + 3]; }
+        if (t > 0 && getenv("B2GP_OZ_PROF"))
+            fprintf(stderr, "[oz prof] per tile: wait MMA %.0f cyc, epilogue %.0f cyc (C update %.0f), tiles %.0f\n", w / t, e / t, u / t, t);
+    }
     return B2GP_OK;
 }

@@ -18,6 +18,13 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// scratch of the int8-split (Ozaki) GEMM path, one per stream: digit planes, row scales, tile list
+struct OzWork {
+    DevBuf planesA, planesB, scaleA, scaleB, prof, tiles;
+    std::vector<int2> order;        // host copy of the tile list (kept alive for the asynchronous upload)
+    int order_tm = -1, order_tn = -1, order_lower = -1;
+};
+
 // One "slot" = the workspace of one posterior draw in flight.
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -27,6 +34,7 @@ struct Slot {
     DevBuf cov;    // P x ldC      posterior covariance / its factor
     DevBuf LinvC;  // inverted diagonal blocks of chol(cov)
     DevBuf misc;   // small scratch
+    OzWork oz;
     cudaEvent_t ev[8];
 };
 
@@ -37,6 +45,7 @@ struct b2gp_ctx {
     size_t mem_bytes = 0;
     int n_streams = 2;
     int use_tma = 1;  // large GEMMs through the TMA / mbarrier persistent kernel (gemm_tma.cuh)
+    int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
     Slot slots[B2GP_MAX_STREAMS];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
     // staging for host-pointer entry points

@@ -1,0 +1,410 @@
+// ozaki.cuh -- fp64 GEMM/SYRK on the int8 tcgen05 tensor cores by integer splitting (Ozaki scheme).
+//
+// sm_100a has no fp64 tcgen05.mma; what it has is kind::i8 with exact int32 accumulation in TMEM at ~16x the
+// DMMA rate.  C[m,n] += alpha * A[m,k] B[n,k]^T is evaluated as follows.
+//   1. slice (oz_slice_kernel): every row of A (and B) is scaled by a power of two 2^-e_i so that |a| < 1 and cut
+//      into S signed base-128 digits d_1..d_S in [-64, 64] (d_1 carries 6 bits, the others 7):
+//         a = 2^e_i * sum_p d_p 2^-w(p),   w(p) = 6 + 7 (p-1)          (exact up to 2^-(6+7(S-1)) ~ 2^-55 for S = 8)
+//      The digits are stored as S int8 planes [S][rows][k], K-major.
+//   2. products (oz_mma_kernel): A_p B_q^T is an int8 GEMM; its int32 result is EXACT (|d d'| <= 2^12, k <= 2^16).
+//      Its weight 2^-(12 + 7 (p+q-2)) depends on t = p+q-2 only, so all pairs of one weight class accumulate into the
+//      same TMEM accumulator.  Classes t >= S are below the target precision and are dropped: S(S+1)/2 products.
+//   3. recombine (epilogue of the same kernel): acc = sum_t 2^-(12+7t) D_t in fp64, smallest class first, and
+//      C[i,j] += alpha * 2^(e_i + f_j) * acc.
+// Kernel organisation (one CTA per SM, persistent):
+//   * output tile 128 x 64: S accumulators of 64 TMEM columns = 512 columns for S = 8 (all of TMEM);
+//   * a pipeline stage is one 64-byte k-block of ALL planes: S boxes [128 rows x 64 B] of A and S boxes
+//     [64 rows x 64 B] of B (TMA, 64-byte swizzle) -- each plane is fetched once per k-block and used by every
+//     pair it takes part in, which is what keeps L2 traffic per fp64-equivalent flop at the DMMA kernel's level;
+//   * warp 0 lane 0: TMA producer; warp 1 lane 0: issues 2 * S(S+1)/2 tcgen05.mma (M=128, N=64, K=32) per stage and
+//     commits to the stage's `empty` mbarrier; warps 2-5: epilogue (tcgen05.ld 32x32b, one TMEM lane = one row each).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm_tma.cuh"
+
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32, OZ_STAGES = 4;   // 32-byte k-blocks (one MMA K step), 4 stages in flight
+constexpr int OZ_THREADS = 192;
+constexpr int OZ_A_TILE = OZ_BM * OZ_KB;  // 8192 B
+constexpr int OZ_B_TILE = OZ_BN * OZ_KB;  // 4096 B
+
+struct OzArgs {
+    int m, n, kb_count;        // kb_count = padded k / OZ_KB
+    int rowsA_pad, rowsB_pad;  // rows of one digit plane (multiple of 128)
+    const double* sa;          // 2^e_i per row of A
+    const double* sb;          // 2^f_j per row of B
+    double* C;
+    int64_t ldc;
+    double alpha;
+    int lower_only;
+    int tiles_m, tiles_n;
+    int num_tiles;
+    const int2* tile_list;  // [num_tiles] (ti, tj) in execution order (host-built, L2-friendly)
+    int debug;  // 0 normal; 1 skip the global read-modify-write; 2 also skip staging barriers (timing experiments only)
+    long long* prof;  // optional [gridDim.x][4]: cycles waiting for acc_full, TMEM drain + fp64 combine, C update, tiles
+};
+
+// ---------------------------------------------------------------------------------------------- slicing
+// one CTA per row: row maximum -> exponent, then S digits per element; planes[p][row][kk]
+template <int S>
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ A, int64_t lda, int rows, int k, int8_t* __restrict__ planes,
+                                                       int rows_pad, int kpad, double* __restrict__ scale) {
+    __shared__ double red[8];
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x;
+    int e = 0;
+    if (row < rows) {
+        double mx = 0.0;
+        for (int kk = tid; kk < k; kk += 256) mx = fmax(mx, fabs(A[(int64_t)row * lda + kk]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((tid & 31) == 0) red[tid >> 5] = mx;
+        __syncthreads();
+        mx = red[0];
+        for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
+        if (mx > 0.0 && mx < 1e300) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+        if (tid == 0) scale[row] = ldexp(1.0, e);
+    }
+    // 4 consecutive k per thread -> one 32-bit store per plane
+    for (int k4 = tid * 4; k4 < kpad; k4 += 1024) {
+        int packed[S];
+#pragma unroll
+        for (int p = 0; p < S; ++p) packed[p] = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = k4 + j;
+            double v = (row < rows && kk < k) ? ldexp(A[(int64_t)row * lda + kk], 6 - e) : 0.0;
+#pragma unroll
+            for (int p = 0; p < S; ++p) {
+                const double d = rint(v);
+                packed[p] |= ((int)d & 0xff) << (8 * j);
+                v = (v - d) * 128.0;
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < S; ++p)
+            *reinterpret_cast<int*>(planes + ((int64_t)p * rows_pad + row) * kpad + k4) = packed[p];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- tcgen05 helpers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, M = 128, N = 64, K = 32
+__device__ __forceinline__ void tc_mma_i8(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(taddr),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor, K-major, 32-byte swizzle (rows of 32 B): 8-row groups are 256 B apart
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);   // start address
+    d |= (uint64_t)0 << 16;                   // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(256 >> 4) << 32;          // stride byte offset
+    d |= (uint64_t)1 << 46;                   // descriptor version (sm_100)
+    d |= (uint64_t)6 << 61;                   // SWIZZLE_32B
+    return d;
+}
+// exact int32 -> double without I2F.F64 (measured: the conversion instruction runs at ~1 per 5 cycles per SM on
+// this part and was the whole epilogue): 2^52 + 2^31 + v is assembled in the mantissa, the constant subtracted.
+__device__ __forceinline__ double i32_to_f64(int v) {
+    return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void oz_tile_of(int x, int lower_only, int tiles_n, int& ti, int& tj) {
+    if (lower_only) {  // 128 x 64 tiles of the lower triangle: row block ti owns column tiles 0 .. 2 ti + 1
+        int t = (int)((sqrt(4.0 * (double)x + 1.0) - 1.0) * 0.5);
+        while ((int64_t)(t + 1) * (t + 2) <= x) ++t;
+        while ((int64_t)t * (t + 1) > x) --t;
+        ti = t;
+        tj = x - t * (t + 1);
+    } else {
+        ti = x / tiles_n;
+        tj = x % tiles_n;
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzArgs p) {
+    constexpr int STAGE_BYTES = S * (OZ_A_TILE + OZ_B_TILE);
+    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + OZ_STAGES * STAGE_BYTES;  // full[2], empty[2], acc_full, acc_empty
+    const uint32_t tmem_slot = bars + 16 * OZ_STAGES + 16;
+    uint8_t* sgen = smem_raw + (base - raw);
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(sgen + OZ_STAGES * STAGE_BYTES + 16 * OZ_STAGES + 16);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t full0 = bars, empty0 = bars + 8 * OZ_STAGES, acc_full = bars + 16 * OZ_STAGES, acc_empty = bars + 16 * OZ_STAGES + 8;
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_gen;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const int2 tt = p.tile_list[tile];
+                const int row0 = tt.x * OZ_BM, col0 = tt.y * OZ_BN;
+                for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+                    const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                    const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int q = 0; q < S; ++q) {
+                        tma_load_2d(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s);
+                        tma_load_2d(st + S * OZ_A_TILE + q * OZ_B_TILE, &mapB, kb * OZ_KB, q * p.rowsB_pad + col0, full0 + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+                mbar_wait(acc_empty, (tcount & 1u) ^ 1u);   // epilogue of the previous tile has drained TMEM
+                tc_fence_after();
+                uint32_t touched = 0;
+                for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+                    const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
+                    mbar_wait(full0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int q = 0; q < S; ++q) {
+#pragma unroll
+                        for (int pp = 0; pp < S - q; ++pp) {
+                            const int t = pp + q;  // weight class
+                            const uint64_t ad = oz_smem_desc(st + pp * OZ_A_TILE);
+                            const uint64_t bd = oz_smem_desc(st + S * OZ_A_TILE + q * OZ_B_TILE);
+                            tc_mma_i8(tmem + 64u * t, ad, bd, IDESC, (touched >> t) & 1u);
+                            touched |= 1u << t;
+                        }
+                    }
+                    tc_commit(empty0 + 8 * s);
+                }
+                tc_commit(acc_full);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: warps 2..5, TMEM lane quarter = warp % 4
+        const int quarter = warp & 3;
+        uint32_t tcount = 0;
+        long long c_wait = 0, c_ld = 0, c_upd = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+            const int2 tt = p.tile_list[tile];
+            const int ti = tt.x, tj = tt.y;
+            const int row = ti * OZ_BM + 32 * quarter + lane;
+            const int col0 = tj * OZ_BN;
+            const long long t0 = clock64();
+            mbar_wait(acc_full, tcount & 1u);
+            tc_fence_after();
+            const long long t1 = clock64();
+            c_wait += t1 - t0;
+            // staging area for one 128 x 16 chunk (stride 17 doubles) + the row scales of this tile
+            double* stg = reinterpret_cast<double*>(sgen + OZ_STAGES * STAGE_BYTES + 128);
+            double* sa_s = stg + 128 * 17;
+            const int et = tid - 64;                      // 0..127 among the epilogue threads
+            const int lrow = 32 * quarter + lane;         // row of the tile this thread drains from TMEM
+            sa_s[lrow] = (row < p.m) ? p.sa[row] * p.alpha : 0.0;
+#pragma unroll 1
+            for (int c16 = 0; c16 < 4; ++c16) {
+                double acc[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+#pragma unroll
+                for (int t = S - 1; t >= 0; --t) {
+                    int v[16];
+                    tc_ld16(tmem + ((uint32_t)(32 * quarter) << 16) + 64u * t + 16u * c16, v);
+                    tc_wait_ld();
+                    const double w = __longlong_as_double((long long)(1023 - (12 + 7 * t)) << 52);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
+                }
+                const long long t2 = clock64();
+                if (p.debug < 2) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous chunk's readers are done with stg
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stg[lrow * 17 + j] = acc[j];
+                if (p.debug < 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+                // coalesced read-modify-write: 16 consecutive threads cover the 128 bytes of one row of the chunk
+                const int cc = et & 15;
+                const int gc = col0 + 16 * c16 + cc;
+                const double sbv = (gc < p.n) ? p.sb[gc] : 0.0;
+                double oldv[16];
+                if (p.debug == 0) {
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                    const int gr = ti * OZ_BM + it * 8 + (et >> 4);
+                    oldv[it] = (gr < p.m && gc < p.n && !(p.lower_only && gc > gr)) ? p.C[(int64_t)gr * p.ldc + gc] : 0.0;
+                }
+#pragma unroll
+                for (int it = 0; it < 16; ++it) {
+                    const int lr = it * 8 + (et >> 4);
+                    const int gr = ti * OZ_BM + lr;
+                    if (gr < p.m && gc < p.n && !(p.lower_only && gc > gr))
+                        p.C[(int64_t)gr * p.ldc + gc] = fma(sa_s[lr] * sbv, stg[lr * 17 + cc], oldv[it]);
+                }
+                }
+                c_upd += clock64() - t2;
+            }
+            tc_fence_before();
+            __syncwarp();
+            c_ld += clock64() - t1;
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        if (p.prof && warp == 2 && lane == 0) {
+            p.prof[4 * blockIdx.x + 0] = c_wait;
+            p.prof[4 * blockIdx.x + 1] = c_ld;     // whole epilogue (drain + combine + C update)
+            p.prof[4 * blockIdx.x + 2] = c_upd;    // of which: C update
+            p.prof[4 * blockIdx.x + 3] = tcount;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+static bool make_tmap_u8(CUtensorMap* map, const int8_t* base, int64_t rows_total, int64_t kpad, int box_rows) {
+    PFN_tmapEncodeTiled enc = tmap_encoder();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)kpad, (cuuint64_t)rows_total};
+    cuuint64_t gstride[1] = {(cuuint64_t)kpad};
+    cuuint32_t box[2] = {(cuuint32_t)OZ_KB, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// C[m,n] += alpha * A[m,k] B[n,k]^T  (lower_only: j <= i, A == B allowed) through the int8 tensor cores
+template <int S>
+static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                         int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
+    if (m <= 0 || n <= 0 || k <= 0) return B2GP_OK;
+    if (k > 32768) return B2GP_ERR_UNSUPPORTED;  // int32 accumulation bound: S * k * 2^12 < 2^31
+    const int64_t kpad = round_up(k, OZ_KB);
+    const int64_t ra = round_up(m, 128), rb = round_up(n, 128);
+    const bool same = (A == B && lda == ldb && m == n);
+    RET_IF(ensure(ctx, w.planesA, (size_t)S * ra * kpad));
+    RET_IF(ensure(ctx, w.scaleA, (size_t)ra * 8));
+    oz_slice_kernel<S><<<(unsigned)ra, 256, 0, st>>>(A, lda, (int)m, (int)k, (int8_t*)w.planesA.p, (int)ra, (int)kpad, (double*)w.scaleA.p);
+    const int8_t* pb = (const int8_t*)w.planesA.p;
+    const double* sb = (const double*)w.scaleA.p;
+    int64_t rbp = ra;
+    if (!same) {
+        RET_IF(ensure(ctx, w.planesB, (size_t)S * rb * kpad));
+        RET_IF(ensure(ctx, w.scaleB, (size_t)rb * 8));
+        oz_slice_kernel<S><<<(unsigned)rb, 256, 0, st>>>(B, ldb, (int)n, (int)k, (int8_t*)w.planesB.p, (int)rb, (int)kpad, (double*)w.scaleB.p);
+        pb = (const int8_t*)w.planesB.p;
+        sb = (const double*)w.scaleB.p;
+        rbp = rb;
+    }
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += same ? 1 : 2;
+    CUtensorMap mapA, mapB;
+    if (!make_tmap_u8(&mapA, (const int8_t*)w.planesA.p, (int64_t)S * ra, kpad, OZ_BM) || !make_tmap_u8(&mapB, pb, (int64_t)S * rbp, kpad, OZ_BN))
+        return B2GP_ERR_UNSUPPORTED;
+    OzArgs a;
+    a.m = (int)m;
+    a.n = (int)n;
+    a.kb_count = (int)(kpad / OZ_KB);
+    a.rowsA_pad = (int)ra;
+    a.rowsB_pad = (int)rbp;
+    a.sa = (const double*)w.scaleA.p;
+    a.sb = sb;
+    a.C = C;
+    a.ldc = ldc;
+    a.alpha = alpha;
+    a.lower_only = lower_only ? 1 : 0;
+    a.tiles_m = (int)ceil_div(m, OZ_BM);
+    a.tiles_n = (int)ceil_div(n, OZ_BN);
+    // Tile order.  One round of the persistent loop runs sm_count consecutive list entries concurrently and, tiles
+    // being equally long, in k-lockstep: if those tiles form a compact block of (row block, column block) pairs, each
+    // operand block is fetched from HBM once per round and served to the other tiles from L2.  Bands of G row blocks,
+    // column-major inside a band: a round covers ~G x (sm_count/G) tiles = G + sm_count/G distinct operand blocks.
+    if (w.order_tm != a.tiles_m || w.order_tn != a.tiles_n || w.order_lower != a.lower_only) {
+        w.order.clear();
+        const int G = 8;
+        for (int b0 = 0; b0 < a.tiles_m; b0 += G) {
+            const int b1 = b0 + G < a.tiles_m ? b0 + G : a.tiles_m;
+            const int tjmax = lower_only ? (2 * (b1 - 1) + 1 < a.tiles_n - 1 ? 2 * (b1 - 1) + 1 : a.tiles_n - 1) : a.tiles_n - 1;
+            for (int tj = 0; tj <= tjmax; ++tj)
+                for (int ti = b0; ti < b1; ++ti)
+                    if (!lower_only || tj <= 2 * ti + 1) w.order.push_back(make_int2(ti, tj));
+        }
+        w.order_tm = a.tiles_m;
+        w.order_tn = a.tiles_n;
+        w.order_lower = a.lower_only;
+        RET_IF(ensure(ctx, w.tiles, w.order.size() * sizeof(int2)));
+        // pageable source: the runtime stages the bytes before returning, and w.order outlives the call anyway
+        CUDA_TRY(ctx, cudaMemcpyAsync(w.tiles.p, w.order.data(), w.order.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    }
+    const int64_t tiles = (int64_t)w.order.size();
+    a.num_tiles = (int)tiles;
+    a.tile_list = (const int2*)w.tiles.p;
+    a.prof = nullptr;
+    if (w.prof.p) a.prof = (long long*)w.prof.p;
+    a.debug = getenv("B2GP_OZ_DEBUG") ? atoi(getenv("B2GP_OZ_DEBUG")) : 0;
+    constexpr int smem_bytes = OZ_STAGES * S * (OZ_A_TILE + OZ_B_TILE) + 128 + (128 * 17 + 128) * 8 + 1024;
+    static bool attr = false;
+    if (!attr) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr = true;
+    }
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    oz_mma_kernel<S><<<grid, OZ_THREADS, smem_bytes, st>>>(mapA, mapB, a);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return B2GP_OK;
+}
+
+static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
+                          const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
+    OzWork* w = &ctx->slots[0].oz;
+    for (int i = 0; i < B2GP_MAX_STREAMS; ++i)
+        if (ctx->slots[i].stream == st) w = &ctx->slots[i].oz;
+    if (ctx->ozaki == 7) return ozaki_gemm_nt<7>(ctx, st, *w, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
+    return ozaki_gemm_nt<8>(ctx, st, *w, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
+}
