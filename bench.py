@@ -14,10 +14,11 @@ Gram(k_XX) -> N x N Cholesky -> Gram(k_pX) -> triangular solves -> posterior mea
   value   posteriors/s with X, y, X_new, theta resident in HBM (device-pointer C-ABI call)
   e2e     the same through the host-buffer C-ABI call (pinned host memory in, host memory out:
           H2D of X, y, X_new, theta and D2H of mean, var, info inside the timed region)
-  roofline  dominant kernel = the DMMA trailing-update GEMM/SYRK (gemm_tma_kernel): algorithmic flops of
-          the top-level SYRK of the N=16384 factorisation (8192 x 8192, k = 8192, lower half) / its
-          CUDA-event duration, against the fp64 GEMM peak measured live with cuBLAS (torch.matmul fp64;
-          MEASURED_PEAKS.json carries no fp64 figure)
+  roofline  dominant kernel = the trailing-update SYRK of the N=16384 factorisation (8192 x 8192, k = 8192, lower half),
+          which runs on the int8 tcgen05 tensor cores (oz_mma_kernel, 8 digit planes = 36 exact int8 GEMMs): achieved int8
+          TOP/s from its CUDA-event duration against 2 x the measured bf16 peak of MEASURED_PEAKS.json; the fp64-equivalent
+          rate and its ratio to the cuBLAS DGEMM rate measured live are reported beside it, and `roofline_dmma` gives the
+          fp64 DMMA kernel on the same launch
   cpu_baseline  the oracle's restatement of the reference formulation (explicit inverse,
           oracle.exact_posterior) timed on the host cores on a bounded sample
 """
@@ -151,19 +152,28 @@ def measure_fp64_peak(local):
 
 
 def measure_dominant_kernel(ctx, ffi):
-    """The trailing-update SYRK at the headline size, device resident, CUDA events around the launch."""
+    """The trailing-update SYRK at the headline size (8192 x 8192, k = 8192, lower half), device resident, CUDA events
+    around the launch(es), through the int8 tcgen05 path (default) and through the fp64 DMMA path."""
     n = 8192
     rng = np.random.default_rng(0)
     A = ctx.to_device(rng.standard_normal((n, n)))
     Cm = ctx.to_device(np.zeros((n, n)))
-    ms = []
-    for _ in range(5):
-        ctx._check(ctx.lib.b2gp_gemm_nt(ctx.h, n, n, n, -1.0, A.ptr, n, A.ptr, n, 1.0, Cm.ptr, n, 1, ffi.FLAG_DEVICE_PTRS))
-        ms.append(ctx.last_timing()["epilogue_ms"])
+    out = {}
+    planes = 8
+    for name, oz in (("dmma", 0), ("tcgen05_i8", planes)):
+        ctx.set_option("ozaki", oz)
+        ms = []
+        for _ in range(5):
+            ctx._check(ctx.lib.b2gp_gemm_nt(ctx.h, n, n, n, -1.0, A.ptr, n, A.ptr, n, 1.0, Cm.ptr, n, 1, ffi.FLAG_DEVICE_PTRS))
+            ms.append(ctx.last_timing()["epilogue_ms"])
+        ms = float(np.mean(ms[2:]))
+        out[name] = {"ms": ms, "fp64_equiv_tflops": float(n) ** 3 / ms / 1e9}
     A.free()
     Cm.free()
-    ms = float(np.mean(ms[2:]))
-    return {"flops_per_launch": float(n) ** 3, "ms": ms, "tflops": float(n) ** 3 / ms / 1e9}
+    out["planes"] = planes
+    out["pairs"] = planes * (planes + 1) // 2
+    out["int8_ops_per_launch"] = out["pairs"] * float(n) ** 3          # 2 * (n*n/2) * n MACs per digit-plane pair
+    return out
 
 
 def cpu_baseline(budget_s=30.0):
@@ -327,19 +337,27 @@ def main():
         if td is not None:
             td.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel, fp64 peak measured live
+    # ---- roofline of the dominant kernel
     dom = measure_dominant_kernel(ctx, ffi)
     try:
-        peak = measure_fp64_peak(local)
+        peak64 = measure_fp64_peak(local)
         peak_src = "cuBLAS DGEMM 8192^3 (torch.matmul fp64) measured in this run; MEASURED_PEAKS.json has no fp64 figure"
     except Exception as e:  # noqa: BLE001
-        peak, peak_src = 35.5, f"fallback 35.5 TFLOP/s (cuBLAS DGEMM measured on this pool, profiles/); live measure failed: {e!r}"
+        peak64, peak_src = 35.5, f"fallback 35.5 TFLOP/s (cuBLAS DGEMM measured on this pool, profiles/); live measure failed: {e!r}"
+    peak = peak64
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        int8_peak, int8_src = 2.0 * float(mp["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops (int8 tcgen05 rate = 2 x bf16), of measured"
+    except Exception:  # noqa: BLE001
+        int8_peak, int8_src = 2.0 * 1590.0, "2 x 1.59 PFLOP/s bf16, of fallback (B200_PROFILING.md)"
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json")))
         traffic = prof.get("dram_bytes_per_launch")
     except Exception:  # noqa: BLE001
         pass
+    oz = dom["tcgen05_i8"]
+    int8_tops = dom["int8_ops_per_launch"] / oz["ms"] / 1e9
     flops_step = S * (N ** 3 / 3 + N * N * (P + 1) + 4 * N * P)
     line = {
         "metric": "gp_posteriors_per_s_N16384", "value": value, "unit": "posteriors/s", "n_gpus": world,
@@ -355,9 +373,18 @@ def main():
         "e2e": {"value": e2e_value, "unit": "posteriors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s", "frac": dom["tflops"] / peak,
-                     "traffic": traffic, "kernel": "gemm_tma_kernel<3,2> (persistent, TMA + mbarrier ring, DMMA.8x8x4; SYRK 8192x8192 k=8192 lower) + 64x64 tail launch",
-                     "flops_per_launch": dom["flops_per_launch"], "ms_per_launch": dom["ms"], "peak_source": peak_src},
+        # dominant kernel: oz_mma_kernel<8> (int8 tcgen05.mma into TMEM, TMA-fed).  Algorithmic work of the launch =
+        # 36 digit-plane-pair int8 GEMMs of the 8192x8192 lower half at k = 8192; denominator = int8 dense tensor peak.
+        "roofline": {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak,
+                     "traffic": traffic, "kernel": "oz_slice_kernel<8> + oz_mma_kernel<8> (UTCIMMA M128 N64 K32, TMEM accumulators, "
+                     "TMA 32B-swizzle stages; SYRK 8192x8192 k=8192 lower)", "int8_ops_per_launch": dom["int8_ops_per_launch"],
+                     "ms_per_launch": oz["ms"], "peak_source": int8_src,
+                     "fp64_equiv_tflops": oz["fp64_equiv_tflops"], "fp64_equiv_over_cublas_dgemm": oz["fp64_equiv_tflops"] / peak64,
+                     "digit_planes": dom["planes"], "plane_pairs": dom["pairs"]},
+        # the fp64 DMMA kernel (gemm_tma_kernel) that the int8 path replaces for large updates, same launch
+        "roofline_dmma": {"bound": "tensor", "achieved": dom["dmma"]["fp64_equiv_tflops"], "peak": peak64, "unit": "TFLOP/s",
+                          "frac": dom["dmma"]["fp64_equiv_tflops"] / peak64, "ms_per_launch": dom["dmma"]["ms"],
+                          "kernel": "gemm_tma_kernel<3,2> (DMMA.8x8x4, TMA + mbarrier) + 64x64 tail launch", "peak_source": peak_src},
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
