@@ -259,6 +259,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--draws", type=int, default=None, help="posterior draws per step (default 8)")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -270,6 +272,11 @@ def main():
     w = WORKLOAD
     ctx = ffi.Context(local)
     ctx.set_option("streams", args.streams)
+    for kv in args.opt:
+        k_, v_ = kv.split("=")
+        ctx.set_option(k_, int(v_))
+    if args.draws:
+        WORKLOAD["S"] = args.draws
     X, y, Xn, theta = make_inputs(rank)
     N, d, P, S = w["N"], w["d"], w["P"], w["S"]
     flags_out = ffi.OUT_MEAN | ffi.OUT_VAR

@@ -152,7 +152,7 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         free_buf(s.oz.scaleA);
         free_buf(s.oz.scaleB);
         free_buf(s.oz.prof);
-        free_buf(s.oz.tiles);
+        for (auto& l : s.oz.lists) free_buf(l.dev);
         for (int e = 0; e < 8; ++e) cudaEventDestroy(s.ev[e]);
         cudaStreamDestroy(s.stream);
     }
@@ -197,6 +197,10 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     if (strcmp(key, "ozaki") == 0) {
         ARG_CHECK(ctx, value == 0 || value == 7 || value == 8);
         ctx->ozaki = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "oz_min_tiles") == 0) {
+        ctx->oz_min_tiles = (int)value;
         return B2GP_OK;
     }
     if (strcmp(key, "tma") == 0) {

@@ -19,10 +19,16 @@ struct DevBuf {
 };
 
 // scratch of the int8-split (Ozaki) GEMM path, one per stream: digit planes, row scales, tile list
+struct OzTileList {
+    int tm = -1, tn = -1, lower = -1;
+    int64_t count = 0;
+    DevBuf dev;
+    std::vector<int2> host;         // kept alive for the asynchronous upload
+};
 struct OzWork {
-    DevBuf planesA, planesB, scaleA, scaleB, prof, tiles;
-    std::vector<int2> order;        // host copy of the tile list (kept alive for the asynchronous upload)
-    int order_tm = -1, order_tn = -1, order_lower = -1;
+    DevBuf planesA, planesB, scaleA, scaleB, prof;
+    OzTileList lists[8];            // the few (tiles_m, tiles_n, lower) shapes one factorisation cycles through
+    int next_list = 0;
 };
 
 // One "slot" = the workspace of one posterior draw in flight.
@@ -45,6 +51,7 @@ struct b2gp_ctx {
     size_t mem_bytes = 0;
     int n_streams = 2;
     int use_tma = 1;  // large GEMMs through the TMA / mbarrier persistent kernel (gemm_tma.cuh)
+    int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
     int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
     Slot slots[B2GP_MAX_STREAMS];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;

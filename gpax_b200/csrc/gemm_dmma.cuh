@@ -252,7 +252,7 @@ static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t
     if (ctx->ozaki && beta == 1.0 && k >= 512 && k <= 32768 && C != A && C != B) {
         const int64_t tm = ceil_div(m, 128), tn = ceil_div(n, 64);
         const int64_t toz = lower_only ? tm * (tm + 1) : tm * tn;
-        if (toz >= 2 * 148) {
+        if (toz >= ctx->oz_min_tiles) {
             const int rc = ozaki_dispatch(ctx, st, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
             if (rc != B2GP_ERR_UNSUPPORTED) return rc;
         }

@@ -364,26 +364,32 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     // being equally long, in k-lockstep: if those tiles form a compact block of (row block, column block) pairs, each
     // operand block is fetched from HBM once per round and served to the other tiles from L2.  Bands of G row blocks,
     // column-major inside a band: a round covers ~G x (sm_count/G) tiles = G + sm_count/G distinct operand blocks.
-    if (w.order_tm != a.tiles_m || w.order_tn != a.tiles_n || w.order_lower != a.lower_only) {
-        w.order.clear();
+    OzTileList* tl = nullptr;
+    for (auto& l : w.lists)
+        if (l.tm == a.tiles_m && l.tn == a.tiles_n && l.lower == a.lower_only) tl = &l;
+    if (!tl) {
+        tl = &w.lists[w.next_list];
+        w.next_list = (w.next_list + 1) % 8;
+        tl->host.clear();
         const int G = 8;
         for (int b0 = 0; b0 < a.tiles_m; b0 += G) {
             const int b1 = b0 + G < a.tiles_m ? b0 + G : a.tiles_m;
             const int tjmax = lower_only ? (2 * (b1 - 1) + 1 < a.tiles_n - 1 ? 2 * (b1 - 1) + 1 : a.tiles_n - 1) : a.tiles_n - 1;
             for (int tj = 0; tj <= tjmax; ++tj)
                 for (int ti = b0; ti < b1; ++ti)
-                    if (!lower_only || tj <= 2 * ti + 1) w.order.push_back(make_int2(ti, tj));
+                    if (!lower_only || tj <= 2 * ti + 1) tl->host.push_back(make_int2(ti, tj));
         }
-        w.order_tm = a.tiles_m;
-        w.order_tn = a.tiles_n;
-        w.order_lower = a.lower_only;
-        RET_IF(ensure(ctx, w.tiles, w.order.size() * sizeof(int2)));
-        // pageable source: the runtime stages the bytes before returning, and w.order outlives the call anyway
-        CUDA_TRY(ctx, cudaMemcpyAsync(w.tiles.p, w.order.data(), w.order.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        tl->tm = a.tiles_m;
+        tl->tn = a.tiles_n;
+        tl->lower = a.lower_only;
+        tl->count = (int64_t)tl->host.size();
+        // a list may still be in use by a kernel queued earlier on this stream: the copy is stream-ordered behind it
+        RET_IF(ensure(ctx, tl->dev, tl->host.size() * sizeof(int2)));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tl->dev.p, tl->host.data(), tl->host.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
     }
-    const int64_t tiles = (int64_t)w.order.size();
+    const int64_t tiles = tl->count;
     a.num_tiles = (int)tiles;
-    a.tile_list = (const int2*)w.tiles.p;
+    a.tile_list = (const int2*)tl->dev.p;
     a.prof = nullptr;
     if (w.prof.p) a.prof = (long long*)w.prof.p;
     a.debug = getenv("B2GP_OZ_DEBUG") ? atoi(getenv("B2GP_OZ_DEBUG")) : 0;
