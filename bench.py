@@ -35,6 +35,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+HOST_MS = []
 WORKLOAD = dict(name="exactgp_rbf_N16384_d3_P1024", N=16384, d=3, P=1024, kernel="RBF", ell=0.3, scale=1.0, noise=0.1,
                 jitter=1e-6, S=8)
 
@@ -292,6 +293,7 @@ def main():
                                           w["jitter"], flags_out | ffi.FLAG_DEVICE_PTRS, dmean.ptr, dvar.ptr, None, None, 0,
                                           None, info.ctypes.data, None))
         t = ctx.last_timing()
+        HOST_MS.append(t["host_enqueue_ms"])
         return t["total_ms"], t["launches"]
 
     for _ in range(max(args.warmup, 3)):
@@ -374,6 +376,7 @@ def main():
                    "outputs": "mean+diag var", "streams": args.streams, "parallelism": f"draw-parallel x{world}",
                    "l2": "inputs larger than L2: each draw rebuilds and factors a 2 GiB K (L2 = 126 MB)"},
         "wall_ms_per_step": wall_ms / args.steps,
+        "host_enqueue_ms_per_step": float(np.mean(HOST_MS[-args.steps:])),
         "fp64_tflops_step": world * flops_step * args.steps / (dev_ms / 1e3) / 1e12,
         "frac_of_chol_roofline_N3_3": (world * S * args.steps * N ** 3 / 3 / (dev_ms / 1e3) / 1e12) / (world * peak),
         "frac_of_chol_roofline_2N3_3": (world * S * args.steps * 2 * N ** 3 / 3 / (dev_ms / 1e3) / 1e12) / (world * peak),

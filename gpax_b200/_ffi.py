@@ -29,7 +29,7 @@ class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("gram_ms", C.c_double), ("potrf_ms", C.c_double),
                 ("trsm_ms", C.c_double), ("epilogue_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("flops", C.c_double), ("gram_bytes", C.c_double),
-                ("launches", C.c_int64)]
+                ("launches", C.c_int64), ("host_enqueue_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -2,6 +2,8 @@
 // reference lines each entry point replaces).  Host code here only orchestrates: workspace, streams,
 // the order of kernel launches.  No torch, no JAX, no CPU fallback: every numerical result is
 // produced by the sm_100a kernels in gram.cuh / gemm_dmma.cuh / potrf.cuh / posterior.cuh.
+#include <chrono>
+
 #include "common.cuh"
 #include "gemm_dmma.cuh"
 #include "gemm_tma.cuh"
@@ -79,7 +81,9 @@ struct CallTimer {
     Extra* ex;
     int64_t launches0;
     CallTimer(b2gp_ctx* c) : ctx(c), ex(extra_of(c)), launches0(c->launches) {}
+    std::chrono::steady_clock::time_point t_begin;
     int begin(cudaStream_t st) {
+        t_begin = std::chrono::steady_clock::now();
         ex->last = b2gp_timing{};
         ex->pool.reset();
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_begin, st));
@@ -87,6 +91,7 @@ struct CallTimer {
     }
     int end(cudaStream_t st, b2gp_timing* out) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_end, st));
+        ex->last.host_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_end));
         float ms = 0.f;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
@@ -197,6 +202,10 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     if (strcmp(key, "ozaki") == 0) {
         ARG_CHECK(ctx, value == 0 || value == 7 || value == 8);
         ctx->ozaki = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "big_grid") == 0) {
+        ctx->big_grid = (int)value;
         return B2GP_OK;
     }
     if (strcmp(key, "oz_min_tiles") == 0) {

@@ -51,6 +51,7 @@ struct b2gp_ctx {
     size_t mem_bytes = 0;
     int n_streams = 2;
     int use_tma = 1;  // large GEMMs through the TMA / mbarrier persistent kernel (gemm_tma.cuh)
+    int big_grid = 0;        // CTAs of the persistent kernels (0 = one per SM); fewer leaves SMs for other streams' small kernels
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
     int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
     Slot slots[B2GP_MAX_STREAMS];

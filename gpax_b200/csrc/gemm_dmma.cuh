@@ -276,7 +276,11 @@ static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t
         // square tiles only for the triangular tile map
         return launch_gemm_cfg<64, 64, 2, 4, 4, 2>(ctx, st, a);
     }
-    const int64_t t64 = ceil_div(m, 64) * tn128;
-    if (t64 >= 112) return launch_gemm_cfg<64, 128, 2, 4, 3, 2>(ctx, st, a);
-    return launch_gemm_cfg<32, 128, 1, 8, 3, 2>(ctx, st, a);
+    // latency-bound regime: minimise (waves) x (time of one tile), in units of a 32x128 tile; the 128x128 kernel holds
+    // one CTA per SM (148 slots), the two smaller ones two (296 slots)
+    const int64_t t64 = ceil_div(m, 64) * tn128, t32 = ceil_div(m, 32) * tn128;
+    const int64_t c128 = ceil_div(t128, 148) * 4, c64 = ceil_div(t64, 296) * 2, c32 = ceil_div(t32, 296) * 1;
+    if (c32 <= c64 && c32 <= c128) return launch_gemm_cfg<32, 128, 1, 8, 3, 2>(ctx, st, a);
+    if (c64 <= c128) return launch_gemm_cfg<64, 128, 2, 4, 3, 2>(ctx, st, a);
+    return launch_gemm_cfg<128, 128, 4, 4, 3, 1>(ctx, st, a);
 }

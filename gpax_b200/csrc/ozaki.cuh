@@ -399,7 +399,8 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = true;
     }
-    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    const int nsm = (ctx->big_grid > 0 && ctx->big_grid < ctx->sm_count) ? ctx->big_grid : ctx->sm_count;
+    const int grid = (int)(tiles < nsm ? tiles : nsm);
     oz_mma_kernel<S><<<grid, OZ_THREADS, smem_bytes, st>>>(mapA, mapB, a);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;

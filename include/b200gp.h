@@ -70,6 +70,7 @@ typedef struct b2gp_timing {
     double flops;        /* algorithmic flops of the call: S * (N^3/3 + N^2 (P+1) + ...)   */
     double gram_bytes;   /* algorithmic bytes written by the Gram builds                                 */
     int64_t launches;    /* kernels launched by the call                                                 */
+    double host_enqueue_ms; /* host wall time spent issuing the call's work (before waiting for the device)  */
 } b2gp_timing;
 
 int  b2gp_version(void);
