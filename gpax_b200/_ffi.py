@@ -67,6 +67,8 @@ SIGNATURES = {
     "b2gp_sparse_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int,
                                         _vp, C.c_int, C.c_double, C.c_uint, _vp, _vp, _vp, _vp, C.POINTER(Timing)]),
     "b2gp_mll": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, C.c_uint, _dp, _vp, _vp, _ip]),
+    "b2gp_sparse_elbo": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, C.c_uint, _dp, _vp,
+                                   _vp, _ip]),
     "b2gp_sparse_partial": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp,
                                       C.c_int64, _vp, _ip]),
     "b2gp_sparse_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int,
@@ -296,6 +298,19 @@ class Context:
         self._check(self.lib.b2gp_mll(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), N, _ptr(yres), d,
                                       _ptr(theta), float(jitter), 0, C.byref(val), _ptr(grad), _ptr(alpha), C.byref(info)))
         return val.value, grad, alpha, info.value
+
+    def sparse_elbo(self, kind, Xu, X, yres, theta, jitter=1e-6):
+        """VFE bound of the sparse GP, its gradient w.r.t. log(lengthscale[d], k_scale, noise, period) and w.r.t. Xu"""
+        Xu, X, yres = _f64(Xu), _f64(X), _f64(yres)
+        M, d = Xu.shape
+        N = X.shape[0]
+        theta = _f64(theta).reshape(d + 3)
+        val, info = C.c_double(0.0), C.c_int(0)
+        g, gx = np.zeros(d + 3), np.zeros((M, d))
+        self._check(self.lib.b2gp_sparse_elbo(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(Xu), M, _ptr(X), N,
+                                              _ptr(yres), d, _ptr(theta), float(jitter), 0, C.byref(val), _ptr(g), _ptr(gx),
+                                              C.byref(info)))
+        return val.value, g, gx, info.value
 
     def sparse_posterior(self, kind, Xu, Xtr, yres, Xnew, theta, noiseless=False, jitter=1e-6, want=("mean", "cov")):
         Xu, Xtr, Xnew = _f64(Xu), _f64(Xtr), _f64(Xnew)

@@ -12,6 +12,7 @@
 #include "mll.cuh"
 #include "posterior.cuh"
 #include "potrf.cuh"
+#include "sparse_elbo.cuh"
 
 // ------------------------------------------------------------------------------------------ helpers
 namespace {
@@ -44,6 +45,7 @@ struct Extra {  // ctx-private state that is not part of the struct the kernels'
     DevBuf potrf_buf;  // staging for host-pointer b2gp_potrf / trsm / gemm
     DevBuf gemm_buf[3];
     std::vector<void*> user_allocs;
+    DevBuf eb[12];     // scratch of b2gp_sparse_elbo
     // factor cache of slot 0 (host-pointer, single-draw calls): predict_in_batches / viGP chunk loops call the
     // posterior repeatedly with the same training set and theta; the reference re-inverts k_XX every time
     // (gp.py:319-322 -> gp.py:269-271), here the factor L and its inverted diagonal blocks are kept.
@@ -1142,6 +1144,144 @@ extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, con
             for (int k = 0; k < nth; ++k) grad[k] = NAN;
     }
     ex->last.flops = (double)N * N * N * (grad ? 1.0 / 3 + 1.0 + 1.0 : 1.0 / 3);
+    return B2GP_OK;
+}
+
+// value and gradient of the VFE bound of the sparse GP (see sparse_elbo.cuh): d/dlog(lengthscale[d], k_scale, noise, period)
+// in grad_theta[d+3] and d/dXu in grad_Xu[M,d].  Xu, X, yres follow `flags`; theta is a HOST pointer; outputs are HOST.
+extern "C" int b2gp_sparse_elbo(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* X, int64_t N, const double* yres,
+                                int d, const double* theta, double jitter, unsigned flags, double* value, double* grad_theta,
+                                double* grad_Xu, int* info) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xu && X && yres && theta && value && grad_theta && grad_Xu && info);
+    ARG_CHECK(ctx, M >= 1 && N >= 1 && d >= 1 && d <= MLL_MAX_D);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    ex->fcache.valid = false;
+    const bool dev = dev_ptrs(flags);
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const int nth = d + 3;
+    const double noise = theta[d + 1], scale = theta[d];
+    const double *dXu, *dX, *dy, *dth;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], X, (size_t)N * d * 8, dev, &dX));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], yres, (size_t)N * 8, dev, &dy));
+    RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, false, &dth));
+    RET_IF(stage_in(ctx, st, ctx->d_in[5], Xu, (size_t)M * d * 8, dev, &dXu));
+    const int64_t ldM = round_up(M, 8), ldN = round_up(N, 8);
+    RET_IF(ensure(ctx, sl.A, (size_t)2 * M * ldM * 8));
+    RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    for (int i = 0; i < 6; ++i) RET_IF(ensure(ctx, ex->eb[i], (size_t)M * ldM * 8));
+    RET_IF(ensure(ctx, ex->eb[6], (size_t)N * ldM * 8));
+    RET_IF(ensure(ctx, ex->eb[7], (size_t)N * ldM * 8));
+    RET_IF(ensure(ctx, ex->eb[8], (size_t)M * ldN * 8));
+    RET_IF(ensure(ctx, ex->eb[9], (size_t)(4 * ldM + 3 * ldN + 64 + M * (nth + d)) * 8));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
+    double* Luu = (double*)sl.A.p;
+    double* Cm = Luu + M * ldM;
+    double* LinvU = (double*)sl.Linv.p;
+    double* LinvC = LinvU + linv_bytes(M) / 8;
+    double *BtU = (double*)ex->eb[0].p, *BtC = (double*)ex->eb[1].p, *Cinv = (double*)ex->eb[2].p;
+    double *T1 = (double*)ex->eb[3].p, *T2 = (double*)ex->eb[4].p, *T3 = (double*)ex->eb[5].p;
+    double *E = (double*)ex->eb[6].p, *GKuft = (double*)ex->eb[7].p, *GKuf = (double*)ex->eb[8].p;
+    double* vec = (double*)ex->eb[9].p;
+    double *bvec = vec, *u = vec + ldM, *beta = vec + 2 * ldM, *tmpM = vec + 3 * ldM;
+    double *tmpN = vec + 4 * ldM, *alpha = tmpN + ldN, *tmpN2 = alpha + ldN;
+    double* scal = tmpN2 + ldN;          // [0] sum log LC_ii, [1] u'u, [2] y'y, [3] |W|_F^2, [4] tr(C^-1), [5] alpha'alpha, [8..] chain
+    double* partial = scal + 64;         // M x (d+3)
+    double* gXu = partial + M * nth;     // M x d
+    dim3 b32(32, 32), gMM((unsigned)ceil_div(M, 32), (unsigned)ceil_div(M, 32));
+
+    // forward pieces shared with the posterior: Luu, W (both layouts), W W^T / noise, W y / noise
+    RET_IF(sparse_partial_dev(ctx, sl, kind, dXu, M, dX, N, dy, d, dth, jitter, noise, Luu, ldM, LinvU, Cm, ldM, bvec, dinfo));
+    double* Wt = (double*)sl.Vt.p;
+    double* W = (double*)sl.cov.p;
+    add_diag_kernel<<<grid_for(M), 256, 0, st>>>(Cm, ldM, M, 1.0);
+    RET_IF(potrf_rec(ctx, st, Cm, ldM, M, LinvC, dinfo + 1, 0));
+    CUDA_TRY(ctx, cudaMemcpyAsync(u, bvec, (size_t)M * 8, cudaMemcpyDeviceToDevice, st));
+    RET_IF(trsm_rec(ctx, st, u, ldM, 1, Cm, ldM, M, LinvC));
+    logdiag_kernel<<<1, 256, 0, st>>>(Cm, ldM, M, scal + 0);
+    rowdot2_kernel<<<1, RD_THREADS, 0, st>>>(u, ldM, M, nullptr, 1.0, nullptr, scal + 1);
+    rowdot2_kernel<<<1, RD_THREADS, 0, st>>>(dy, ldN, N, nullptr, 1.0, nullptr, scal + 2);
+    rowdot2_kernel<<<(unsigned)M, RD_THREADS, 0, st>>>(W, ldN, N, nullptr, 1.0, nullptr, tmpM);
+    vecsum_kernel<<<1, 256, 0, st>>>(tmpM, M, scal + 3);
+    // C^{-1} = BtC BtC^T with BtC = (LC^{-1})^T, beta = C^{-1} b
+    set_identity_kernel<<<grid_for(M * M), 256, 0, st>>>(BtC, ldM, M);
+    RET_IF(trsm_rec(ctx, st, BtC, ldM, M, Cm, ldM, M, LinvC));
+    rowdot2_kernel<<<(unsigned)M, RD_THREADS, 0, st>>>(BtC, ldM, M, u, 1.0, beta, tmpM);
+    vecsum_kernel<<<1, 256, 0, st>>>(tmpM, M, scal + 4);
+    RET_IF(gemm_nt(ctx, st, M, M, M, 1.0, BtC, ldM, BtC, ldM, 0.0, Cinv, ldM, true));
+    mirror_lower_kernel<<<gMM, b32, 0, st>>>(Cinv, ldM, M);
+    // alpha = (y - W^T beta) / noise
+    rowdot2_kernel<<<(unsigned)N, RD_THREADS, 0, st>>>(Wt, ldM, M, beta, 1.0, tmpN, nullptr);
+    elbo_alpha_kernel<<<grid_for(N), 256, 0, st>>>(alpha, dy, tmpN, N, noise);
+    rowdot2_kernel<<<1, RD_THREADS, 0, st>>>(alpha, ldN, N, nullptr, 1.0, nullptr, scal + 5);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 14;
+    // the clip of the trace term decides a coefficient of the reverse pass: fetch the scalars now
+    double hs[8];
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs, scal, sizeof hs, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    double kd = scale;
+    if (kind == B2GP_KERNEL_MATERN52) {
+        const double r = sqrt(1e-12), s5r = 2.23606797749979 * r;
+        kd = scale * (1.0 + s5r) * exp(-s5r);
+    }
+    const double T = (double)N * kd - hs[3];
+    const double coef = (T > 0.0) ? 1.0 : 0.0;
+    // dELBO/dW^T = alpha beta^T + (coef W^T - W^T C^{-1}) / noise
+    RET_IF(gemm_nt(ctx, st, N, M, M, 1.0, Wt, ldM, Cinv, ldM, 0.0, E, ldM, false));
+    elbo_gw_kernel<<<grid_for(N * M), 256, 0, st>>>(E, ldM, Wt, ldM, alpha, beta, N, M, coef, noise);
+    // dELBO/dKuf^T = (dELBO/dW^T) Luu^{-1}
+    set_identity_kernel<<<grid_for(M * M), 256, 0, st>>>(BtU, ldM, M);
+    RET_IF(trsm_rec(ctx, st, BtU, ldM, M, Luu, ldM, M, LinvU));
+    RET_IF(gemm_nt(ctx, st, N, M, M, 1.0, E, ldM, BtU, ldM, 0.0, GKuft, ldM, false));
+    {
+        dim3 g((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32)), b(32, 8);
+        transpose_kernel<<<g, b, 0, st>>>(GKuf, ldN, GKuft, ldM, N, M);
+    }
+    // H^T = W G_Kuf^T; G_L = -tril(H); dELBO/dKuu = Luu^{-T} Phi(Luu^T G_L) Luu^{-1}
+    RET_IF(gemm_nt(ctx, st, M, M, N, 1.0, W, ldN, GKuf, ldN, 0.0, T1, ldM, false));
+    tri_kernel<<<gMM, b32, 0, st>>>(T2, ldM, T1, ldM, M, 1);              // T2 = G_L^T = -triu(H^T)
+    tri_kernel<<<gMM, b32, 0, st>>>(T3, ldM, Luu, ldM, M, 0);             // T3 = tril(Luu)
+    {
+        dim3 b(32, 8);
+        transpose_kernel<<<gMM, b, 0, st>>>(T1, ldM, T3, ldM, M, M);      // T1 = Luu^T
+    }
+    RET_IF(gemm_nt(ctx, st, M, M, M, 1.0, T1, ldM, T2, ldM, 0.0, T3, ldM, false));   // T3 = Luu^T G_L
+    tri_kernel<<<gMM, b32, 0, st>>>(T2, ldM, T3, ldM, M, 2);              // T2 = Phi(.)
+    RET_IF(gemm_nt(ctx, st, M, M, M, 1.0, BtU, ldM, T2, ldM, 0.0, T1, ldM, false));  // T1 = BtU P^T
+    RET_IF(gemm_nt(ctx, st, M, M, M, 1.0, BtU, ldM, T1, ldM, 0.0, T3, ldM, false));  // T3 = dELBO/dKuu
+    tri_kernel<<<gMM, b32, 0, st>>>(T2, ldM, T3, ldM, M, 3);              // T2 = T3 + T3^T
+    // contract with the kernel derivatives
+    elbo_chain_kernel<<<(unsigned)M, 256, 0, st>>>(kind, d, dth, dXu, (int)M, dX, N, GKuf, ldN, GKuf, ldN, 0, 0, partial, gXu);
+    elbo_chain_kernel<<<(unsigned)M, 256, 0, st>>>(kind, d, dth, dXu, (int)M, dXu, M, T3, ldM, T2, ldM, 1, 1, partial, gXu);
+    colsum_kernel<<<1, 32, 0, st>>>(partial, M, nth, scal + 8);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 12;
+    double hs2[8 + MLL_MAX_D + 3];
+    int hinfo[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(hs2, scal, sizeof hs2, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(grad_Xu, gXu, (size_t)M * d * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(hinfo, dinfo, sizeof hinfo, cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    *info = hinfo[0] != 0 ? hinfo[0] : -hinfo[1];
+    const double n = (double)N, m = (double)M;
+    const double loglik = -0.5 * (n * 1.8378770664093453 + n * log(noise) + 2.0 * hs2[0] + hs2[2] / noise - hs2[1]);
+    *value = loglik - 0.5 * (T > 0.0 ? T / noise : 0.0);
+    for (int k = 0; k < nth; ++k) grad_theta[k] = hs2[8 + k];
+    grad_theta[d] += (T > 0.0) ? -0.5 * n * kd / noise : 0.0;
+    const double trSinv = (n - m + hs2[4]) / noise;
+    grad_theta[d + 1] = noise * (-0.5 * trSinv + 0.5 * hs2[5] + ((T > 0.0) ? 0.5 * T / (noise * noise) : 0.0));
+    if (*info != 0) {
+        *value = NAN;
+        for (int k = 0; k < nth; ++k) grad_theta[k] = NAN;
+    }
     return B2GP_OK;
 }
 

@@ -61,7 +61,7 @@ class LogJoint:
     def __call__(self, u, jacobian):
         """log p(y | theta(u)) + sum log p(theta_k) [+ log |dtheta/du| if jacobian]; returns (value, grad_u)"""
         th = self.theta_of(u)
-        val, g, _, info = self.m.ctx.mll(self.kind, self.X, self.y, th, self.jitter, want_grad=True)
+        val, g, info = self._lik(th)
         self.n_evals += 1
         if info != 0 or not np.isfinite(val):
             return -np.inf, np.zeros(self.dim)
@@ -75,6 +75,11 @@ class LogJoint:
                 val += float(pr.log_abs_jac(u[k]))
                 grad[k] += float(pr.dlog_abs_jac(u[k]))
         return val, grad
+
+    def _lik(self, th):
+        """log p(y | theta) and its gradient w.r.t. log(theta): the exact marginal likelihood (b2gp_mll)"""
+        val, g, _, info = self.m.ctx.mll(self.kind, self.X, self.y, th, self.jitter, want_grad=True)
+        return val, g, info
 
     def to_dict(self, U):
         """rows of unconstrained vectors -> dict of constrained samples with the reference's site names / shapes"""
@@ -126,10 +131,60 @@ def fit_vi_gp(model, rng_key, num_steps, step_size, progress_bar, **kwargs):
     return SVIState(np.array(losses), "normal" if normal else "delta", loc, np.exp(params[lj.dim:]) if normal else None), med
 
 
+class SparseLogJoint(LogJoint):
+    """LogJoint whose likelihood term is the VFE bound of viSparseGP.model (sparse_gp.py:62-114) at the current
+    inducing inputs `self.Xu`; the gradient w.r.t. Xu of the last evaluation is left in `self.grad_Xu`."""
+
+    def __init__(self, model, Xu, jitter=1e-6):
+        super().__init__(model, jitter)
+        self.Xu = np.array(Xu, dtype=np.float64, copy=True)
+        if self.Xu.ndim == 1:
+            self.Xu = self.Xu[:, None]
+        self.grad_Xu = np.zeros_like(self.Xu)
+
+    def _lik(self, th):
+        val, g, gx, info = self.m.ctx.sparse_elbo(self.kind, self.Xu, self.X, self.y, th, self.jitter)
+        self.grad_Xu = gx
+        return val, g, info
+
+
 def fit_sparse_gp(model, rng_key, Xu0, num_steps, step_size, progress_bar, **kwargs):
-    raise NotImplementedError(
-        "viSparseGP.fit (VFE ELBO with learnable inducing points, gpax/models/sparse_gp.py:62-171) is not built yet: "
-        "set m.X_train, m.y_train, m.Xu and pass params to predict / get_mvn_posterior")
+    """sparse_gp.py:116-171: SVI with Adam(b1=0.5) over the hyper-parameters (delta or normal guide, as viGP) and over
+    the inducing inputs Xu (a plain parameter, no prior).  Returns (state, dict with the guide median and 'Xu')."""
+    lj = SparseLogJoint(model, Xu0, kwargs.get("jitter", 1e-6))
+    rng = seed_from_key(rng_key)
+    normal = model.guide_type == "normal"
+    nu = lj.dim
+    loc = lj.init_u()
+    rho = np.full(nu, math.log(0.1))
+    head = np.concatenate([loc, rho]) if normal else loc.copy()
+    params = np.concatenate([head, lj.Xu.ravel()])
+    nh = head.size
+    m1, m2 = np.zeros_like(params), np.zeros_like(params)
+    b1, b2, eps = 0.5, 0.999, 1e-8
+    losses = []
+    for t in range(1, int(num_steps) + 1):
+        lj.Xu = params[nh:].reshape(lj.Xu.shape)
+        if normal:
+            mu, r = params[:nu], params[nu:nh]
+            e = rng.standard_normal(nu)
+            val, g = lj(mu + np.exp(r) * e, jacobian=True)
+            elbo = val + r.sum() + 0.5 * nu * (1 + math.log(2 * math.pi))
+            ghead = np.concatenate([g, g * e * np.exp(r) + 1.0])
+        else:
+            elbo, ghead = lj(params[:nu], jacobian=False)
+        grad = np.concatenate([ghead, lj.grad_Xu.ravel()])
+        losses.append(-elbo)
+        if not np.isfinite(elbo):
+            grad = np.zeros_like(params)
+        m1 = b1 * m1 + (1 - b1) * (-grad)
+        m2 = b2 * m2 + (1 - b2) * grad * grad
+        params = params - step_size * (m1 / (1 - b1 ** t)) / (np.sqrt(m2 / (1 - b2 ** t)) + eps)
+        if progress_bar and (t % max(1, num_steps // 10) == 0 or t == num_steps):
+            print(f"svi step {t}/{num_steps}  loss {losses[-1]:.4f}")
+    med = {k: v[0] for k, v in lj.to_dict(params[:nu]).items()}
+    med["Xu"] = params[nh:].reshape(lj.Xu.shape)
+    return SVIState(np.array(losses), "normal" if normal else "delta", params[:nu], np.exp(params[nu:nh]) if normal else None), med
 
 
 # ---------------------------------------------------------------------------------------------- NUTS

@@ -31,7 +31,7 @@ class viSparseGP(viGP):
         Xu0 = initialize_inducing_points(np.array(X, copy=True), inducing_points_ratio, inducing_points_selection, rng_key)
         self.X_train, self.y_train = X, y
         self.svi, self.kernel_params = fit_sparse_gp(self, rng_key, Xu0, num_steps, step_size, progress_bar, **kwargs)
-        self.Xu = self.kernel_params["Xu"]
+        self.Xu = self.kernel_params.pop("Xu")
         if print_summary:
             self._print_summary()
 

@@ -169,6 +169,15 @@ int  b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double*
               const double* theta, double jitter, unsigned flags,
               double* value, double* grad, double* alpha_out, int* info);
 
+/* Fit side of the sparse GP: the VFE bound of viSparseGP.model (gpax/models/sparse_gp.py:62-114)
+ *   log LowRankMVN(yres; 0, W^T W + noise I) - 1/2 clip(sum_n (Kff_nn - Qff_nn) / noise, 0),  W = Luu^{-1} K(Xu, X)
+ * and its gradient w.r.t. (log lengthscale[d], log k_scale, log noise, log period) in grad_theta[d+3] and w.r.t. the
+ * inducing inputs in grad_Xu[M,d] (the reference differentiates the same expression with JAX; Xu is a numpyro.param,
+ * sparse_gp.py:69-70).  theta is a HOST pointer; value / grads are HOST outputs; Xu, X, yres follow `flags`. d <= 16.  */
+int  b2gp_sparse_elbo(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* X, int64_t N,
+                      const double* yres, int d, const double* theta, double jitter, unsigned flags,
+                      double* value, double* grad_theta, double* grad_Xu, int* info);
+
 /* ---- multi-GPU building blocks.  One process per GPU; the exchange steps
  * (panel broadcast, M x M all-reduce) are issued by the host side over NCCL on these same device
  * buffers (gpax_b200/distributed.py).  All array pointers below are DEVICE pointers. ----------------*/

@@ -140,3 +140,69 @@ def test_predict_in_batches_reuses_factor():
     mean2, _ = m.predict(0, Xt, params)
     ref, _ = oracle.vi_predict(X + 0.01, y, Xt, params, "Matern")
     np.testing.assert_allclose(mean2, ref, rtol=1e-8, atol=1e-9)
+
+
+# ------------------------------------------------------------------ sparse GP: VFE bound and its gradients
+def elbo_ref(kind, X, y, Xu, theta, jitter):
+    """NumPy restatement of viSparseGP.model's score (gpax/models/sparse_gp.py:91-114) for a small problem"""
+    from scipy.stats import multivariate_normal
+    d = X.shape[1]
+    params = {"k_length": theta[:d], "k_scale": theta[d], "period": theta[d + 2]}
+    noise = theta[d + 1]
+    k = KMAP[kind]
+    Luu = sla.cholesky(k(Xu, Xu, params, 0.0, jitter=jitter), lower=True)
+    W = sla.solve_triangular(Luu, k(Xu, X, params, 0.0, jitter=0.0), lower=True)
+    kd = k(X[:1], X[:1], params, 0.0, jitter=0.0)[0, 0]
+    trace_term = max((len(y) * kd - (W ** 2).sum()) / noise, 0.0)
+    S = W.T @ W + noise * np.eye(len(y))
+    return multivariate_normal(np.zeros(len(y)), S).logpdf(y) - 0.5 * trace_term
+
+
+@pytest.mark.parametrize("kind,d,N,M", [("RBF", 1, 60, 7), ("Matern", 2, 150, 20), ("Periodic", 1, 80, 9)])
+def test_sparse_elbo_value_and_gradients(kind, d, N, M):
+    import gpax_b200
+    ctx = gpax_b200.default_context()
+    rng = np.random.default_rng(N + M)
+    X = rng.uniform(0, 2, (N, d))
+    y = np.sin(3 * X[:, 0]) + 0.2 * rng.standard_normal(N)
+    Xu = X[rng.choice(N, M, replace=False)] + 0.01 * rng.standard_normal((M, d))
+    theta = np.concatenate([rng.uniform(0.5, 0.9, d), [1.3, 0.15, 1.3]])
+    val, g, gx, info = ctx.sparse_elbo(kind, Xu, X, y, theta, 1e-5)
+    assert info == 0
+    ref = elbo_ref(kind, X, y, Xu, theta, 1e-5)
+    assert abs(val - ref) <= 1e-8 * abs(ref), (val, ref)
+    idx = list(range(d + 2)) + ([d + 2] if kind == "Periodic" else [])
+    h = 1e-5
+    for k in idx:
+        tp, tm = theta.copy(), theta.copy()
+        tp[k] *= np.exp(h)
+        tm[k] *= np.exp(-h)
+        num = (elbo_ref(kind, X, y, Xu, tp, 1e-5) - elbo_ref(kind, X, y, Xu, tm, 1e-5)) / (2 * h)
+        assert abs(g[k] - num) <= 1e-4 * max(1.0, abs(num)), ("theta", k, g[k], num)
+    for (a, k) in [(0, 0), (M // 2, d - 1), (M - 1, 0)]:
+        Xp, Xm = Xu.copy(), Xu.copy()
+        Xp[a, k] += h
+        Xm[a, k] -= h
+        num = (elbo_ref(kind, X, y, Xp, theta, 1e-5) - elbo_ref(kind, X, y, Xm, theta, 1e-5)) / (2 * h)
+        assert abs(gx[a, k] - num) <= 1e-4 * max(1.0, abs(num)), ("Xu", a, k, gx[a, k], num)
+
+
+def test_visparsegp_fit_then_predict():
+    """tests/test_sparsegp.py:26-44 contract: fit sets m.Xu, more steps move it; prediction is sensible"""
+    import gpax_b200
+    rng = np.random.default_rng(0)
+    X = np.sort(rng.uniform(0, 4, 200))
+    y = np.sin(2 * X) + 0.1 * rng.standard_normal(200)
+    m = gpax_b200.viSparseGP(1, "RBF")
+    m.fit(0, X, y, inducing_points_ratio=0.1, num_steps=1, step_size=0.02, progress_bar=False, print_summary=False)
+    Xu1 = np.array(m.Xu)
+    assert Xu1.shape == (20, 1)
+    m.fit(0, X, y, inducing_points_ratio=0.1, num_steps=300, step_size=0.02, progress_bar=False, print_summary=False)
+    assert not np.allclose(m.Xu, Xu1)
+    assert m.svi.losses[-10:].mean() < m.svi.losses[:10].mean()
+    assert set(m.kernel_params) == {"k_length", "k_scale", "noise"}
+    Xt = np.linspace(0.2, 3.8, 40)
+    mean, var = m.predict(0, Xt, noiseless=True)
+    assert np.abs(mean - np.sin(2 * Xt)).max() < 0.25 and (var > 0).all()
+    mean2, cov2 = m.get_mvn_posterior(Xt, m.get_samples(), noiseless=True)
+    np.testing.assert_allclose(mean2, mean, rtol=1e-9, atol=1e-10)
