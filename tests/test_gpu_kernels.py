@@ -118,6 +118,34 @@ def test_gemm_large_tma_path(ctx, m, n, k, lower):
     np.testing.assert_array_equal(C, C2)
 
 
+@pytest.mark.parametrize("m,n,k,lower", [(2500, 1300, 700, False), (3000, 3000, 1536, True), (1025, 8192, 4096, False)])
+def test_int8_tcgen05_gemm(ctx, m, n, k, lower):
+    """the rank-k update through the int8 digit-plane kernel (ozaki.cuh): rows of very different magnitude (each row
+    carries its own power-of-two scale), ragged m / n / k; error measured against |a_i| |b_j| like a DGEMM's"""
+    rng = np.random.default_rng(m + n + k)
+    A = rng.standard_normal((m, k)) * np.exp(rng.normal(0, 3, (m, 1)))
+    B = A if lower else rng.standard_normal((n, k)) * np.exp(rng.normal(0, 3, (n, 1)))
+    C0 = rng.standard_normal((m, n))
+    ref = C0 - A @ B.T
+    # a DGEMM-style bound: rounding of the product (|a_i| |b_j|) plus rounding of the update of C itself
+    scale = np.linalg.norm(A, axis=1)[:, None] * np.linalg.norm(B, axis=1)[None, :] + np.abs(C0) + np.abs(ref)
+    errs = {}
+    for planes in (0, 8, 7):
+        ctx.set_option("ozaki", planes)
+        C = ctx.gemm_nt(A, B, C0, alpha=-1.0, beta=1.0, lower_only=lower)
+        mask = np.tril(np.ones((m, n), bool)) if lower else np.ones((m, n), bool)
+        errs[planes] = (np.abs(C - ref) / scale)[mask].max()
+        if lower:
+            np.testing.assert_array_equal(C[~mask], C0[~mask])
+    ctx.set_option("ozaki", 8)
+    assert errs[0] <= 3e-15 and errs[8] <= 2e-14 and errs[7] <= 5e-13, errs
+    # alpha, and a B different from A with lower_only off
+    C = ctx.gemm_nt(A, B, C0, alpha=0.5, beta=1.0, lower_only=lower)
+    ref2 = C0 + 0.5 * A @ B.T
+    scale2 = scale + np.abs(ref2)
+    assert (np.abs(C - ref2) / scale2)[np.tril(np.ones((m, n), bool)) if lower else np.ones((m, n), bool)].max() <= 2e-14
+
+
 # ------------------------------------------------------------------ Cholesky + triangular solve
 @pytest.mark.parametrize("n", [1, 2, 31, 64, 65, 127, 128, 129, 200, 256, 300, 511, 777, 1024, 1500, 4100])
 def test_potrf(ctx, n):
