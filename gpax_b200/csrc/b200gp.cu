@@ -3,6 +3,7 @@
 // the order of kernel launches.  No torch, no JAX, no CPU fallback: every numerical result is
 // produced by the sm_100a kernels in gram.cuh / gemm_dmma.cuh / potrf.cuh / posterior.cuh.
 #include <chrono>
+#include <thread>
 
 #include "common.cuh"
 #include "gemm_dmma.cuh"
@@ -39,7 +40,7 @@ struct EventPool {
 struct Extra {  // ctx-private state that is not part of the struct the kernels' headers see
     EventPool pool;
     b2gp_timing last{};
-    cudaEvent_t slot_done[B2GP_MAX_STREAMS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t slot_done[B2GP_MAX_STREAMS] = {};
     cudaEvent_t inputs_ready = nullptr;
     DevBuf theta1;     // one-draw theta for b2gp_gram
     DevBuf potrf_buf;  // staging for host-pointer b2gp_potrf / trsm / gemm
@@ -91,9 +92,13 @@ struct CallTimer {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_begin, st));
         return B2GP_OK;
     }
+    // host time spent queueing work so far (call before any copy into pageable memory, which blocks the host)
+    void mark_enqueued() {
+        ex->last.host_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    }
     int end(cudaStream_t st, b2gp_timing* out) {
         CUDA_TRY(ctx, cudaEventRecord(ctx->ev_end, st));
-        ex->last.host_enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        if (ex->last.host_enqueue_ms == 0.0) mark_enqueued();
         CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_end));
         float ms = 0.f;
         CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
@@ -204,6 +209,10 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     if (strcmp(key, "ozaki") == 0) {
         ARG_CHECK(ctx, value == 0 || value == 7 || value == 8);
         ctx->ozaki = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "enqueue_threads") == 0) {
+        ctx->enqueue_threads = value != 0;
         return B2GP_OK;
     }
     if (strcmp(key, "big_grid") == 0) {
@@ -585,7 +594,8 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
         ex->fcache.valid = false;
     }
 
-    for (int64_t s = 0; s < S; ++s) {
+    // One draw's whole pipeline, queued on its slot's stream.  Returns a B2GP_* code.
+    auto enqueue_draw = [&](int64_t s) -> int {
         Slot& sl = ctx->slots[s % nslots];
         cudaStream_t st = sl.stream;
         double* A = (double*)sl.A.p;
@@ -660,7 +670,28 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
             }
         }
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[5], st));
+        return B2GP_OK;
+    };
+    // A draw is ~1.4k launches at N=16384 and the driver lets the host run only ~1k launches ahead of the device, so a
+    // single queueing thread feeds the slots one after the other and their streams barely overlap.  One host thread
+    // per slot keeps every stream's queue full (the slots share nothing but read-only inputs).
+    if (ctx->enqueue_threads && nslots > 1 && S > nslots && !timing) {
+        std::vector<int> rcs((size_t)nslots, B2GP_OK);
+        std::vector<std::thread> workers;
+        for (int q = 0; q < nslots; ++q)
+            workers.emplace_back([&, q] {
+                if (cudaSetDevice(ctx->device) != cudaSuccess) {
+                    rcs[q] = B2GP_ERR_CUDA;
+                    return;
+                }
+                for (int64_t s = q; s < S && rcs[q] == B2GP_OK; s += nslots) rcs[q] = enqueue_draw(s);
+            });
+        for (auto& w : workers) w.join();
+        for (int q = 0; q < nslots; ++q) RET_IF(rcs[q]);
+    } else {
+        for (int64_t s = 0; s < S; ++s) RET_IF(enqueue_draw(s));
     }
+    tm.mark_enqueued();
     // ---- join the slots on stream 0
     for (int q = 1; q < nslots; ++q) {
         CUDA_TRY(ctx, cudaEventRecord(ex->slot_done[q], ctx->slots[q].stream));

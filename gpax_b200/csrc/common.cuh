@@ -1,6 +1,7 @@
 // common.cuh -- context, error handling, device buffers for libb200gp.so (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 
 #include <cstdint>
 #include <cstdio>
@@ -10,7 +11,7 @@
 
 #include "../../include/b200gp.h"
 
-#define B2GP_MAX_STREAMS 4
+#define B2GP_MAX_STREAMS 8
 #define B2GP_LEAF 128  // diagonal-block size of the factorisation (one CTA, shared memory)
 
 struct DevBuf {
@@ -51,6 +52,7 @@ struct b2gp_ctx {
     size_t mem_bytes = 0;
     int n_streams = 2;
     int use_tma = 1;  // large GEMMs through the TMA / mbarrier persistent kernel (gemm_tma.cuh)
+    int enqueue_threads = 1;  // queue the draws of a multi-draw posterior from one host thread per slot
     int big_grid = 0;        // CTAs of the persistent kernels (0 = one per SM); fewer leaves SMs for other streams' small kernels
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
     int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
@@ -63,7 +65,7 @@ struct b2gp_ctx {
     // factor bookkeeping for b2gp_trsm_lower (host-pointer mode keeps the factor resident)
     DevBuf last_linv;
     int64_t last_n = 0;
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};  // kernels queued (draws may be queued from several host threads)
     std::string err;
 };
 

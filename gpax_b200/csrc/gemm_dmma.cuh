@@ -210,7 +210,7 @@ static int launch_gemm_cfg(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     if (grid <= 0) return B2GP_OK;
     auto kern = aligned ? gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true, MINB>
                         : gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, false, MINB>;
-    static bool attr_set[2] = {false, false};
+    static std::atomic<bool> attr_set[2];  // zero-initialised
     if (!attr_set[aligned ? 1 : 0]) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set[aligned ? 1 : 0] = true;

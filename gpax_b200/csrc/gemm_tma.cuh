@@ -28,16 +28,14 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_tmapEncodeTiled tmap_encoder() {
-    static PFN_tmapEncodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    static const PFN_tmapEncodeTiled fn = [] {  // initialised once, thread-safe
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (PFN_tmapEncodeTiled)p;
-    }
+            return (PFN_tmapEncodeTiled)p;
+        return (PFN_tmapEncodeTiled) nullptr;
+    }();
     return fn;
 }
 
@@ -238,7 +236,7 @@ static int launch_gemm_tma(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     a.tiles_n = (a.n + TG_BN - 1) / TG_BN;
     const int64_t tiles = a.lower_only ? (int64_t)a.tiles_m * (a.tiles_m + 1) / 2 : (int64_t)a.tiles_m * a.tiles_n;
     if (tiles <= 0) return B2GP_OK;
-    static bool attr = false;
+    static std::atomic<bool> attr{false};
     if (!attr) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tma_kernel<STAGES, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = true;
@@ -261,7 +259,7 @@ static int launch_gemm_tma(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
         t.tiles_n = (a.n + 63) / 64;
         constexpr int tail_smem = 4 * (64 + 64) * GEMM_LDS * (int)sizeof(double);
         auto kern = gemm_nt_kernel<64, 64, 2, 4, 4, true, 2>;
-        static bool tattr = false;
+        static std::atomic<bool> tattr{false};
         if (!tattr) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem));
             tattr = true;

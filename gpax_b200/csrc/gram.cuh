@@ -359,7 +359,7 @@ static int launch_gram(b2gp_ctx* ctx, cudaStream_t st, int kind, const double* X
     a.K = K;
     a.ldk = ldk;
     const size_t smem = (size_t)(GRAM_BM * d + GRAM_BM + d * GRAM_BN + GRAM_BN + d) * sizeof(double);
-    static bool attr = false;
+    static std::atomic<bool> attr{false};
     if (!attr) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
         attr = true;

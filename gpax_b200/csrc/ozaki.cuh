@@ -13,11 +13,14 @@
 //      C[i,j] += alpha * 2^(e_i + f_j) * acc.
 // Kernel organisation (one CTA per SM, persistent):
 //   * output tile 128 x 64: S accumulators of 64 TMEM columns = 512 columns for S = 8 (all of TMEM);
-//   * a pipeline stage is one 64-byte k-block of ALL planes: S boxes [128 rows x 64 B] of A and S boxes
-//     [64 rows x 64 B] of B (TMA, 64-byte swizzle) -- each plane is fetched once per k-block and used by every
-//     pair it takes part in, which is what keeps L2 traffic per fp64-equivalent flop at the DMMA kernel's level;
-//   * warp 0 lane 0: TMA producer; warp 1 lane 0: issues 2 * S(S+1)/2 tcgen05.mma (M=128, N=64, K=32) per stage and
-//     commits to the stage's `empty` mbarrier; warps 2-5: epilogue (tcgen05.ld 32x32b, one TMEM lane = one row each).
+//   * a pipeline stage is one 32-byte k-block (one MMA K step) of ALL planes: S boxes [128 rows x 32 B] of A and S
+//     boxes [64 rows x 32 B] of B (TMA, 32-byte swizzle), 4 stages in flight -- each plane is fetched once per
+//     k-block and used by every pair it takes part in, which keeps L2 traffic per fp64-equivalent flop at the DMMA
+//     kernel's level;
+//   * warp 0 lane 0: TMA producer; warp 1 lane 0: MMA issuer.  The S(S+1)/2 products of a stage are issued as
+//     12 (S = 8) wide tcgen05.mma: A plane p against the stacked B planes 0..S-1-p (M = 128, N up to 256, K = 32),
+//     landing in the adjacent accumulators p..S-1; then commit to the stage's `empty` mbarrier;
+//   * warps 2-5: epilogue (tcgen05.ld 32x32b, one TMEM lane = one row each).
 #pragma once
 #include <cuda.h>
 
@@ -26,8 +29,8 @@
 
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32, OZ_STAGES = 4;   // 32-byte k-blocks (one MMA K step), 4 stages in flight
 constexpr int OZ_THREADS = 192;
-constexpr int OZ_A_TILE = OZ_BM * OZ_KB;  // 8192 B
-constexpr int OZ_B_TILE = OZ_BN * OZ_KB;  // 4096 B
+constexpr int OZ_A_TILE = OZ_BM * OZ_KB;  // 4096 B
+constexpr int OZ_B_TILE = OZ_BN * OZ_KB;  // 2048 B
 
 struct OzArgs {
     int m, n, kb_count;        // kb_count = padded k / OZ_KB
@@ -147,7 +150,6 @@ template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzArgs p) {
     constexpr int STAGE_BYTES = S * (OZ_A_TILE + OZ_B_TILE);
-    constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -203,22 +205,28 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
                 mbar_wait(acc_empty, (tcount & 1u) ^ 1u);   // epilogue of the previous tile has drained TMEM
                 tc_fence_after();
-                uint32_t touched = 0;
                 for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
                     tc_fence_after();
                     const uint32_t st = base + s * STAGE_BYTES;
+                    // Digit plane pp of A meets planes q = 0 .. S-1-pp of B, and the product (pp, q) belongs to weight class
+                    // pp + q = accumulator columns 64 (pp + q).  The B planes of a stage are contiguous in shared memory
+                    // (a [64 S] x 32 B K-major operand) and so are the accumulators, so ONE MMA with N = 64 (S - pp) does
+                    // all of plane pp's products (two when N > 256).  Besides cutting the instruction count 3x this
+                    // reads the 4 KB A plane from shared memory once per 2-4 products instead of once per product:
+                    // with N = 64 per MMA the operand reads (6 KB / 32 cycles) exceed the 128 B/clk of shared memory.
 #pragma unroll
-                    for (int q = 0; q < S; ++q) {
-#pragma unroll
-                        for (int pp = 0; pp < S - q; ++pp) {
-                            const int t = pp + q;  // weight class
-                            const uint64_t ad = oz_smem_desc(st + pp * OZ_A_TILE);
-                            const uint64_t bd = oz_smem_desc(st + S * OZ_A_TILE + q * OZ_B_TILE);
-                            tc_mma_i8(tmem + 64u * t, ad, bd, IDESC, (touched >> t) & 1u);
-                            touched |= 1u << t;
-                        }
+                    for (int pp = 0; pp < S; ++pp) {
+                        const uint64_t ad = oz_smem_desc(st + pp * OZ_A_TILE);
+                        const uint32_t acc = (kb > 0 || pp > 0) ? 1u : 0u;   // plane 0 touches every class first
+                        constexpr uint32_t IDESC_BASE = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BM >> 4) << 24);
+                        const int nq = S - pp;                                // number of B planes
+                        const int n1 = nq > 4 ? 4 : nq;
+                        tc_mma_i8(tmem + 64u * pp, ad, oz_smem_desc(st + S * OZ_A_TILE), IDESC_BASE | ((uint32_t)(n1 * OZ_BN >> 3) << 17), acc);
+                        if (nq > 4)
+                            tc_mma_i8(tmem + 64u * (pp + 4), ad, oz_smem_desc(st + S * OZ_A_TILE + 4 * OZ_B_TILE),
+                                      IDESC_BASE | ((uint32_t)((nq - 4) * OZ_BN >> 3) << 17), acc);
                     }
                     tc_commit(empty0 + 8 * s);
                 }
@@ -394,7 +402,7 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     if (w.prof.p) a.prof = (long long*)w.prof.p;
     a.debug = getenv("B2GP_OZ_DEBUG") ? atoi(getenv("B2GP_OZ_DEBUG")) : 0;
     constexpr int smem_bytes = OZ_STAGES * S * (OZ_A_TILE + OZ_B_TILE) + 128 + (128 * 17 + 128) * 8 + 1024;
-    static bool attr = false;
+    static std::atomic<bool> attr{false};
     if (!attr) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = true;

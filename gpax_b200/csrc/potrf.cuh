@@ -387,7 +387,7 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int n, double* __restrict
 
 static int potrf_diag(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int n, double* Linv_blk, int* info,
                       int index_base) {
-    static bool attr = false;
+    static std::atomic<bool> attr{false};
     if (!attr) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
         attr = true;
