@@ -45,7 +45,7 @@ struct OzArgs {
     int num_tiles;
     const int2* tile_list;  // [num_tiles] (ti, tj) in execution order (host-built, L2-friendly)
     int debug;  // 0 normal; 1 skip the global read-modify-write; 2 also skip staging barriers (timing experiments only)
-    long long* prof;  // optional [gridDim.x][4]: cycles waiting for acc_full, TMEM drain + fp64 combine, C update, tiles
+    long long* prof;  // optional [gridDim.x][8]: epilogue cycles (wait acc_full, whole, C update), tiles, MMA issuer (wait TMA, wait drain, total)
 };
 
 // ---------------------------------------------------------------------------------------------- slicing
@@ -131,6 +131,29 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, int (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 consecutive accumulator columns of this thread's TMEM lane.  The registers are valid only after tc_wait_ld32,
+// which names them as operands so that no use can be scheduled above the wait.
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld32(int (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void oz_tile_of(int x, int lower_only, int tiles_n, int& ti, int& tj) {
@@ -202,12 +225,18 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             uint32_t it = 0, tcount = 0;
+            long long m_full = 0, m_empty = 0;
+            const long long m_t0 = clock64();
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+                const long long e0 = clock64();
                 mbar_wait(acc_empty, (tcount & 1u) ^ 1u);   // epilogue of the previous tile has drained TMEM
+                m_empty += clock64() - e0;
                 tc_fence_after();
                 for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
+                    const long long f0 = p.prof ? clock64() : 0;
                     mbar_wait(full0 + 8 * s, ph);
+                    if (p.prof) m_full += clock64() - f0;
                     tc_fence_after();
                     const uint32_t st = base + s * STAGE_BYTES;
                     // Digit plane pp of A meets planes q = 0 .. S-1-pp of B, and the product (pp, q) belongs to weight class
@@ -232,6 +261,11 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 }
                 tc_commit(acc_full);
             }
+            if (p.prof) {
+                p.prof[8 * blockIdx.x + 4] = m_full;               // MMA issuer: waiting for TMA data
+                p.prof[8 * blockIdx.x + 5] = m_empty;              // ... for the epilogue to drain TMEM
+                p.prof[8 * blockIdx.x + 6] = clock64() - m_t0;     // ... whole loop
+            }
         }
     } else {
         // ------------------------------------------------------------ epilogue: warps 2..5, TMEM lane quarter = warp % 4
@@ -243,67 +277,89 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const int ti = tt.x, tj = tt.y;
             const int row = ti * OZ_BM + 32 * quarter + lane;
             const int col0 = tj * OZ_BN;
+            // coalesced mapping of the C update: 16 consecutive threads cover the 128 bytes of one row of a 16-column chunk
+            const int et = tid - 64;                      // 0..127 among the epilogue threads
+            const int cc = et & 15;
             const long long t0 = clock64();
             mbar_wait(acc_full, tcount & 1u);
             tc_fence_after();
             const long long t1 = clock64();
             c_wait += t1 - t0;
+            // pull the tile of C towards L2 now: the drain below takes longer than an HBM round trip
+            if (p.debug == 0 && (cc == 0 || cc == 15)) {
+#pragma unroll
+                for (int c16 = 0; c16 < 4; ++c16) {
+                    const int gc = col0 + 16 * c16 + cc;
+#pragma unroll
+                    for (int it = 0; it < 16; ++it) {
+                        const int gr = ti * OZ_BM + it * 8 + (et >> 4);
+                        if (gr < p.m && gc < p.n && !(p.lower_only && col0 + 16 * c16 > gr)) prefetch_l2(p.C + (int64_t)gr * p.ldc + gc);
+                    }
+                }
+            }
             // staging area for one 128 x 16 chunk (stride 17 doubles) + the row scales of this tile
             double* stg = reinterpret_cast<double*>(sgen + OZ_STAGES * STAGE_BYTES + 128);
             double* sa_s = stg + 128 * 17;
-            const int et = tid - 64;                      // 0..127 among the epilogue threads
             const int lrow = 32 * quarter + lane;         // row of the tile this thread drains from TMEM
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the previous tile's last chunk is done with sa_s / stg
             sa_s[lrow] = (row < p.m) ? p.sa[row] * p.alpha : 0.0;
-#pragma unroll 1
-            for (int c16 = 0; c16 < 4; ++c16) {
-                double acc[16];
+            // ---- drain: all S accumulators of this row, smallest weight class first, 32 columns per tcgen05.ld; the
+            // load of the next block is in flight while the current one is converted and accumulated
+            double acc[64];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+            for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+            {
+                int v[2][32];
+                const uint32_t trow = tmem + ((uint32_t)(32 * quarter) << 16);
+                tc_ld32(trow + 64u * (S - 1), v[0]);
+                tc_wait_ld32(v[0]);
 #pragma unroll
-                for (int t = S - 1; t >= 0; --t) {
-                    int v[16];
-                    tc_ld16(tmem + ((uint32_t)(32 * quarter) << 16) + 64u * t + 16u * c16, v);
-                    tc_wait_ld();
+                for (int nb = 0; nb < 2 * S; ++nb) {
+                    const int t = S - 1 - (nb >> 1), h = nb & 1;
+                    if (nb + 1 < 2 * S) tc_ld32(trow + 64u * (S - 1 - ((nb + 1) >> 1)) + 32u * ((nb + 1) & 1), v[(nb + 1) & 1]);
                     const double w = __longlong_as_double((long long)(1023 - (12 + 7 * t)) << 52);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[j] = fma(i32_to_f64(v[j]), w, acc[j]);
+                    for (int j = 0; j < 32; ++j) acc[32 * h + j] = fma(i32_to_f64(v[nb & 1][j]), w, acc[32 * h + j]);
+                    if (nb + 1 < 2 * S) tc_wait_ld32(v[(nb + 1) & 1]);
                 }
-                const long long t2 = clock64();
-                if (p.debug < 2) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous chunk's readers are done with stg
-#pragma unroll
-                for (int j = 0; j < 16; ++j) stg[lrow * 17 + j] = acc[j];
-                if (p.debug < 2) asm volatile("bar.sync 1, 128;" ::: "memory");
-                // coalesced read-modify-write: 16 consecutive threads cover the 128 bytes of one row of the chunk
-                const int cc = et & 15;
-                const int gc = col0 + 16 * c16 + cc;
-                const double sbv = (gc < p.n) ? p.sb[gc] : 0.0;
-                double oldv[16];
-                if (p.debug == 0) {
-#pragma unroll
-                for (int it = 0; it < 16; ++it) {
-                    const int gr = ti * OZ_BM + it * 8 + (et >> 4);
-                    oldv[it] = (gr < p.m && gc < p.n && !(p.lower_only && gc > gr)) ? p.C[(int64_t)gr * p.ldc + gc] : 0.0;
-                }
-#pragma unroll
-                for (int it = 0; it < 16; ++it) {
-                    const int lr = it * 8 + (et >> 4);
-                    const int gr = ti * OZ_BM + lr;
-                    if (gr < p.m && gc < p.n && !(p.lower_only && gc > gr))
-                        p.C[(int64_t)gr * p.ldc + gc] = fma(sa_s[lr] * sbv, stg[lr * 17 + cc], oldv[it]);
-                }
-                }
-                c_upd += clock64() - t2;
             }
+            // TMEM is drained: the next tile's MMAs run while this one is written out
             tc_fence_before();
             __syncwarp();
-            c_ld += clock64() - t1;
             if (lane == 0) mbar_arrive(acc_empty);
+            const long long t2 = clock64();
+#pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) {
+                if (c16 > 0 && p.debug < 2) asm volatile("bar.sync 1, 128;" ::: "memory");   // previous chunk's readers are done with stg
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stg[lrow * 17 + j] = acc[16 * c16 + j];
+                if (p.debug < 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int gc = col0 + 16 * c16 + cc;
+                const double sbv = (gc < p.n) ? p.sb[gc] : 0.0;
+                if (p.debug == 0) {
+                    double oldv[16];
+#pragma unroll
+                    for (int it = 0; it < 16; ++it) {
+                        const int gr = ti * OZ_BM + it * 8 + (et >> 4);
+                        oldv[it] = (gr < p.m && gc < p.n && !(p.lower_only && gc > gr)) ? p.C[(int64_t)gr * p.ldc + gc] : 0.0;
+                    }
+#pragma unroll
+                    for (int it = 0; it < 16; ++it) {
+                        const int lr = it * 8 + (et >> 4);
+                        const int gr = ti * OZ_BM + lr;
+                        if (gr < p.m && gc < p.n && !(p.lower_only && gc > gr))
+                            p.C[(int64_t)gr * p.ldc + gc] = fma(sa_s[lr] * sbv, stg[lr * 17 + cc], oldv[it]);
+                    }
+                }
+            }
+            c_upd += clock64() - t2;
+            c_ld += clock64() - t1;
         }
         if (p.prof && warp == 2 && lane == 0) {
-            p.prof[4 * blockIdx.x + 0] = c_wait;
-            p.prof[4 * blockIdx.x + 1] = c_ld;     // whole epilogue (drain + combine + C update)
-            p.prof[4 * blockIdx.x + 2] = c_upd;    // of which: C update
-            p.prof[4 * blockIdx.x + 3] = tcount;
+            p.prof[8 * blockIdx.x + 0] = c_wait;
+            p.prof[8 * blockIdx.x + 1] = c_ld;     // whole epilogue (drain + combine + C update)
+            p.prof[8 * blockIdx.x + 2] = c_upd;    // of which: C update
+            p.prof[8 * blockIdx.x + 3] = tcount;
         }
     }
     tc_fence_before();
@@ -407,7 +463,7 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = true;
     }
-    const int nsm = (ctx->big_grid > 0 && ctx->big_grid < ctx->sm_count) ? ctx->big_grid : ctx->sm_count;
+    const int nsm = persist_sms(ctx, st);
     const int grid = (int)(tiles < nsm ? tiles : nsm);
     oz_mma_kernel<S><<<grid, OZ_THREADS, smem_bytes, st>>>(mapA, mapB, a);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -417,9 +473,8 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
 
 static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
                           const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
-    OzWork* w = &ctx->slots[0].oz;
-    for (int i = 0; i < B2GP_MAX_STREAMS; ++i)
-        if (ctx->slots[i].stream == st) w = &ctx->slots[i].oz;
+    Slot* sl = slot_of(ctx, st);
+    OzWork* w = sl ? &sl->oz : &ctx->slots[0].oz;
     if (ctx->ozaki == 7) return ozaki_gemm_nt<7>(ctx, st, *w, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
     return ozaki_gemm_nt<8>(ctx, st, *w, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
 }

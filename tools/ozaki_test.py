@@ -56,8 +56,9 @@ if mode == "small":
         run(S, 512, 512, 200, True, True)
         run(S, 1024, 1024, 1024, True, True)
 elif mode == "prof":
-    run(8, 8192, 8192, 512, True, True, check=False, reps=1)
-    run(8, 8192, 8192, 4096, True, True, check=False, reps=1)
+    for kk in (512, 2048, 8192):
+        run(8, 8192, 8192, kk, True, True, check=False, reps=2)
+    run(8, 8192, 8192, 2048, False, False, check=False, reps=2)
 else:
     for S in (8, 7):
         run(S, 4096, 4096, 4096, True, True, check=True, reps=2)
