@@ -110,79 +110,6 @@ struct CallTimer {
 };
 
 
-// ------------------------------------------------------------------------------------------ SM-partitioned lanes
-// Driver entry points are fetched at run time (the library does not link libcuda).
-namespace {
-template <class F>
-F drv(const char* name) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
-    return (F)p;
-}
-}  // namespace
-
-static void lanes_destroy(b2gp_ctx* ctx) {
-    for (int i = 0; i < B2GP_MAX_STREAMS; ++i) {
-        Slot& sl = ctx->slots[i];
-        if (sl.small) cudaStreamDestroy(sl.small);
-        if (sl.big) cudaStreamDestroy(sl.big);
-        if (sl.ev_fork) cudaEventDestroy(sl.ev_fork);
-        if (sl.ev_join) cudaEventDestroy(sl.ev_join);
-        sl.small = sl.big = nullptr;
-        sl.ev_fork = sl.ev_join = nullptr;
-    }
-    auto destroy = drv<CUresult (*)(CUgreenCtx)>("cuGreenCtxDestroy");
-    if (destroy) {
-        if (ctx->green_small) destroy((CUgreenCtx)ctx->green_small);
-        if (ctx->green_big) destroy((CUgreenCtx)ctx->green_big);
-    }
-    ctx->green_small = ctx->green_big = nullptr;
-    ctx->lanes_small_sms = ctx->lanes_big_sms = 0;
-}
-
-// Split the SMs into a small partition (`want_small` SMs, rounded by the driver to its granularity) and the rest, one
-// green context each, and give every slot one stream in each.  Returns B2GP_ERR_UNSUPPORTED when the driver cannot.
-static int lanes_init(b2gp_ctx* ctx, int want_small) {
-    if (ctx->lanes_small_sms > 0 && ctx->lanes == want_small) return B2GP_OK;
-    lanes_destroy(ctx);
-    auto getres = drv<CUresult (*)(CUdevice, CUdevResource*, CUdevResourceType)>("cuDeviceGetDevResource");
-    auto split = drv<CUresult (*)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int)>(
-        "cuDevSmResourceSplitByCount");
-    auto gendesc = drv<CUresult (*)(CUdevResourceDesc*, CUdevResource*, unsigned int)>("cuDevResourceGenerateDesc");
-    auto gcreate = drv<CUresult (*)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int)>("cuGreenCtxCreate");
-    auto screate = drv<CUresult (*)(CUstream*, CUgreenCtx, unsigned int, int)>("cuGreenCtxStreamCreate");
-    if (!getres || !split || !gendesc || !gcreate || !screate)
-        return set_err(ctx, B2GP_ERR_UNSUPPORTED, "lanes", "green-context driver API not available", __FILE__, __LINE__);
-    CUdevResource all, small, rest;
-    unsigned int groups = 1;
-    CUdevice dev = (CUdevice)ctx->device;
-    CUdevResourceDesc dsmall, dbig;
-    CUgreenCtx gsmall = nullptr, gbig = nullptr;
-    if (getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS || split(&small, &groups, &all, &rest, 0, (unsigned)want_small) != CUDA_SUCCESS ||
-        groups < 1 || gendesc(&dsmall, &small, 1) != CUDA_SUCCESS || gendesc(&dbig, &rest, 1) != CUDA_SUCCESS ||
-        gcreate(&gsmall, dsmall, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS || gcreate(&gbig, dbig, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS)
-        return set_err(ctx, B2GP_ERR_UNSUPPORTED, "lanes", "SM partitioning failed", __FILE__, __LINE__);
-    ctx->green_small = gsmall;
-    ctx->green_big = gbig;
-    for (int i = 0; i < B2GP_MAX_STREAMS; ++i) {
-        Slot& sl = ctx->slots[i];
-        CUstream a = nullptr, b = nullptr;
-        if (screate(&a, gsmall, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS || screate(&b, gbig, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) {
-            lanes_destroy(ctx);
-            return set_err(ctx, B2GP_ERR_UNSUPPORTED, "lanes", "cuGreenCtxStreamCreate failed", __FILE__, __LINE__);
-        }
-        sl.small = (cudaStream_t)a;
-        sl.big = (cudaStream_t)b;
-        cudaEventCreateWithFlags(&sl.ev_fork, cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming);
-    }
-    ctx->lanes_small_sms = (int)small.sm.smCount;
-    ctx->lanes_big_sms = (int)rest.sm.smCount;
-    ctx->lanes = want_small;
-    return B2GP_OK;
-}
-
 // ------------------------------------------------------------------------------------------ lifecycle
 extern "C" int b2gp_version(void) { return B2GP_VERSION; }
 
@@ -225,7 +152,6 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     Extra* ex = extra_of(ctx);
-    lanes_destroy(ctx);
     for (int i = 0; i < B2GP_MAX_STREAMS; ++i) {
         Slot& s = ctx->slots[i];
         free_buf(s.A);
@@ -286,16 +212,10 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
         ctx->ozaki = (int)value;
         return B2GP_OK;
     }
-    if (strcmp(key, "lanes") == 0) {
-        ARG_CHECK(ctx, value >= 0 && value < ctx->sm_count);
-        CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-        CUDA_TRY(ctx, cudaDeviceSynchronize());
-        if (value == 0) {
-            lanes_destroy(ctx);
-            ctx->lanes = 0;
-            return B2GP_OK;
-        }
-        return lanes_init(ctx, (int)value);
+    if (strcmp(key, "oz_cluster") == 0) {
+        ARG_CHECK(ctx, value == 1 || value == 2);
+        ctx->oz_cluster = (int)value;
+        return B2GP_OK;
     }
     if (strcmp(key, "enqueue_threads") == 0) {
         ctx->enqueue_threads = value != 0;
@@ -598,14 +518,7 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     cudaStream_t st0 = ctx->slots[0].stream;
     CallTimer tm(ctx);
     RET_IF(tm.begin(st0));
-    // several draws in flight: queue each on its slot's small-lane stream and let gemm_nt / launch_gram move the
-    // machine-filling kernels to the big lane (common.cuh: lane_enter)
-    struct LaneGuard {
-        b2gp_ctx* c;
-        ~LaneGuard() { c->lanes_active = false; }
-    } lane_guard{ctx};
-    ctx->lanes_active = ctx->lanes_small_sms > 0 && nslots > 1;
-    auto slot_stream = [&](int q) { return ctx->lanes_active ? ctx->slots[q].small : ctx->slots[q].stream; };
+    auto slot_stream = [&](int q) { return ctx->slots[q].stream; };
 
     // ---- inputs
     const int nth = d + 3;
@@ -721,14 +634,10 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
         // mean / var
         double* mean_s = want_mean ? dmean + s * P : (double*)sl.misc.p;
         if (want_mean || want_var || want_samp) {
-            cudaStream_t run;
-            Slot* lane;
-            RET_IF(lane_enter(ctx, st, lane_is_big(ctx, P), &run, &lane));
-            rowdot_kernel<<<(unsigned)P, RD_THREADS, 0, run>>>(Vt, ldV, N, P, kind, d, th, noise_mult_new, jitter, inf, mean_s,
-                                                            want_var ? dvar + s * P : nullptr);
+            rowdot_kernel<<<(unsigned)P, RD_THREADS, 0, st>>>(Vt, ldV, N, P, kind, d, th, noise_mult_new, jitter, inf, mean_s,
+                                                           want_var ? dvar + s * P : nullptr);
             CUDA_TRY(ctx, cudaGetLastError());
             ctx->launches++;
-            RET_IF(lane_leave(ctx, st, lane));
         }
         if (need_cov) {
             // cov = k_pp - V^T V  (gp.py:267, 272), lower tiles then mirrored -> exactly symmetric

@@ -21,7 +21,7 @@ struct DevBuf {
 
 // scratch of the int8-split (Ozaki) GEMM path, one per stream: digit planes, row scales, tile list
 struct OzTileList {
-    int tm = -1, tn = -1, lower = -1;
+    int tm = -1, tn = -1, lower = -1, cl = -1;
     int64_t count = 0;
     DevBuf dev;
     std::vector<int2> host;         // kept alive for the asynchronous upload
@@ -35,10 +35,6 @@ struct OzWork {
 // One "slot" = the workspace of one posterior draw in flight.
 struct Slot {
     cudaStream_t stream = nullptr;
-    // SM-partitioned lanes (green contexts, see lanes_init in b200gp.cu): `small` runs the latency-bound chain of a draw
-    // (diagonal blocks, thin GEMMs) on a few reserved SMs, `big` the machine-filling kernels on the rest
-    cudaStream_t small = nullptr, big = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf A;      // N x ldA      k_XX, then its factor L (lower)
     DevBuf Vt;     // (P+1) x ldV  rows 0..P-1 = k_pX (gp.py:268), row P = y_res; then V^T, w^T
     DevBuf Linv;   // nblk x 128 x 128 inverted diagonal blocks of L
@@ -57,12 +53,9 @@ struct b2gp_ctx {
     int n_streams = 2;
     int use_tma = 1;  // large GEMMs through the TMA / mbarrier persistent kernel (gemm_tma.cuh)
     int enqueue_threads = 1;  // queue the draws of a multi-draw posterior from one host thread per slot
-    int lanes = 0;            // SMs reserved for the small lane of multi-draw posteriors (0 = no partitioning)
-    int lanes_small_sms = 0, lanes_big_sms = 0;
-    bool lanes_active = false;  // set while a multi-draw posterior is being queued on the partitioned streams
-    void *green_small = nullptr, *green_big = nullptr;
     int big_grid = 0;        // CTAs of the persistent kernels (0 = one per SM); fewer leaves SMs for other streams' small kernels
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
+    int oz_cluster = 2;  // 2: CTA pairs share the A digit planes by TMA multicast; 1: independent CTAs
     int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
     Slot slots[B2GP_MAX_STREAMS];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
@@ -121,46 +114,13 @@ static inline int ensure(b2gp_ctx* ctx, DevBuf& b, size_t bytes) {
 }
 
 static inline Slot* slot_of(b2gp_ctx* ctx, cudaStream_t st) {
-    for (int i = 0; i < B2GP_MAX_STREAMS; ++i) {
-        Slot& sl = ctx->slots[i];
-        if (sl.stream == st || (st && (sl.small == st || sl.big == st))) return &sl;
-    }
+    for (int i = 0; i < B2GP_MAX_STREAMS; ++i)
+        if (ctx->slots[i].stream == st) return &ctx->slots[i];
     return nullptr;
 }
 
-// CTAs a persistent (one CTA per SM) kernel should launch on `st`
-static inline int persist_sms(b2gp_ctx* ctx, cudaStream_t st) {
-    if (ctx->lanes_active) {
-        Slot* sl = slot_of(ctx, st);
-        if (sl && sl->big && st == sl->big) return ctx->lanes_big_sms;
-        if (sl && sl->small && st == sl->small) return ctx->lanes_small_sms;
-    }
-    return (ctx->big_grid > 0 && ctx->big_grid < ctx->sm_count) ? ctx->big_grid : ctx->sm_count;
-}
-
-// Lane hand-off.  A draw's work is queued on its slot's `small` stream; a machine-filling kernel is moved to the
-// slot's `big` stream (the other SM partition) between two event edges, so that other draws' thin kernels keep
-// running beside it instead of queueing behind its CTAs.
-static inline int lane_enter(b2gp_ctx* ctx, cudaStream_t st, bool want_big, cudaStream_t* run, Slot** lane) {
-    *run = st;
-    *lane = nullptr;
-    if (!want_big || !ctx->lanes_active) return B2GP_OK;
-    Slot* sl = slot_of(ctx, st);
-    if (!sl || !sl->big || st != sl->small) return B2GP_OK;
-    CUDA_TRY(ctx, cudaEventRecord(sl->ev_fork, st));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(sl->big, sl->ev_fork, 0));
-    *run = sl->big;
-    *lane = sl;
-    return B2GP_OK;
-}
-static inline int lane_leave(b2gp_ctx* ctx, cudaStream_t st, Slot* lane) {
-    if (!lane) return B2GP_OK;
-    CUDA_TRY(ctx, cudaEventRecord(lane->ev_join, lane->big));
-    CUDA_TRY(ctx, cudaStreamWaitEvent(st, lane->ev_join, 0));
-    return B2GP_OK;
-}
-// thin enough for the small lane?  (CTAs of the 32x128 configuration against what the reserved SMs hold)
-static inline bool lane_is_big(b2gp_ctx* ctx, int64_t ctas) { return ctas > (int64_t)4 * ctx->lanes_small_sms; }
+// CTAs a persistent (one CTA per SM) kernel should launch
+static inline int persist_sms(b2gp_ctx* ctx) { return (ctx->big_grid > 0 && ctx->big_grid < ctx->sm_count) ? ctx->big_grid : ctx->sm_count; }
 
 static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }

@@ -228,21 +228,9 @@ static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, 
 // C = beta*C + alpha*A*B^T.  lower_only requires a square C (m == n) whose diagonal is the matrix
 // diagonal.  `inplace_rows` marks the B <- B*Linv^T use where C aliases A: that is only safe with a
 // single column tile (n <= 128), which the 128-wide configuration guarantees.
-static int gemm_nt_on(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only);
-
 static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                    int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
     if (m <= 0 || n <= 0) return B2GP_OK;
-    cudaStream_t run;
-    Slot* lane;
-    RET_IF(lane_enter(ctx, st, ctx->lanes_active && lane_is_big(ctx, ceil_div(m, 32) * ceil_div(n, 128)), &run, &lane));
-    RET_IF(gemm_nt_on(ctx, run, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, lower_only));
-    return lane_leave(ctx, st, lane);
-}
-
-static int gemm_nt_on(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                      const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
     GemmArgs a;
     a.m = (int)m;
     a.n = (int)n;

@@ -244,7 +244,7 @@ static int launch_gemm_tma(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     // Wave quantisation: with T tiles on S SMs the persistent kernel takes ceil(T/S) tile-times.  The T mod S tiles
     // of the last, partial wave are handed to a follow-up launch as 64x64 quarters (2 CTAs/SM): a quarter of the
     // work per CTA on four times the CTAs, so the tail costs ~0.3-0.6 tile-times instead of 1.
-    const int S = persist_sms(ctx, st);
+    const int S = persist_sms(ctx);
     int64_t main_tiles = tiles;
     if (tiles > S && tiles % S != 0) main_tiles = tiles - tiles % S;
     const int grid = (int)(main_tiles < S ? main_tiles : S);

@@ -365,14 +365,11 @@ static int launch_gram(b2gp_ctx* ctx, cudaStream_t st, int kind, const double* X
         attr = true;
     }
     dim3 grid((unsigned)ceil_div(m, GRAM_BN), (unsigned)ceil_div(n, GRAM_BM));
-    cudaStream_t run;
-    Slot* lane;
-    RET_IF(lane_enter(ctx, st, ctx->lanes_active && lane_is_big(ctx, (int64_t)grid.x * grid.y), &run, &lane));
     bool done = false;
-    if (kind == B2GP_KERNEL_RBF) done = launch_gram_fast<B2GP_KERNEL_RBF>(run, a, grid);
-    if (kind == B2GP_KERNEL_MATERN52) done = launch_gram_fast<B2GP_KERNEL_MATERN52>(run, a, grid);
-    if (!done) gram_kernel<<<grid, GRAM_THREADS, smem, run>>>(a);
+    if (kind == B2GP_KERNEL_RBF) done = launch_gram_fast<B2GP_KERNEL_RBF>(st, a, grid);
+    if (kind == B2GP_KERNEL_MATERN52) done = launch_gram_fast<B2GP_KERNEL_MATERN52>(st, a, grid);
+    if (!done) gram_kernel<<<grid, GRAM_THREADS, smem, st>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
-    return lane_leave(ctx, st, lane);
+    return B2GP_OK;
 }

@@ -94,6 +94,28 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
 // ---------------------------------------------------------------------------------------------- tcgen05 helpers
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// commit that arrives on the barrier at the same shared-memory offset in every CTA of `mask` (cluster of 2)
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+// TMA box load delivered to the same shared-memory offset (and signalling the same barrier offset) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -169,9 +191,15 @@ __device__ __forceinline__ void oz_tile_of(int x, int lower_only, int tiles_n, i
     }
 }
 
-template <int S>
+// CL = 2: the two CTAs of a cluster work on column tiles 2 j and 2 j + 1 of the same row block.  They need the same A
+// digit planes, so each CTA fetches half of them and TMA multicasts every box into both shared memories (the L2 -> SM
+// operand traffic, which is what bounds this kernel, drops from 48 to 32 KB per CTA and k-block).  A stage may be
+// refilled only when BOTH CTAs have consumed it: the `empty` barriers count two commits, one multicast from each.
+template <int S, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzArgs p) {
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
+    const int tile_first = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     constexpr int STAGE_BYTES = S * (OZ_A_TILE + OZ_B_TILE);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -186,7 +214,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CL);
         }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
@@ -198,6 +226,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
 
@@ -205,17 +234,20 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
                 const int2 tt = p.tile_list[tile];
-                const int row0 = tt.x * OZ_BM, col0 = tt.y * OZ_BN;
+                const int row0 = tt.x * OZ_BM, col0 = (CL * tt.y + (int)crank) * OZ_BN;
                 for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+                    mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);   // bytes landing in THIS CTA's stage, whoever fetches them
                     const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
                     for (int q = 0; q < S; ++q) {
-                        tma_load_2d(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s);
+                        if (CL == 1)
+                            tma_load_2d(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s);
+                        else if ((q < (S + 1) / 2) == (crank == 0))
+                            tma_load_2d_mc(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s, (uint16_t)3);
                         tma_load_2d(st + S * OZ_A_TILE + q * OZ_B_TILE, &mapB, kb * OZ_KB, q * p.rowsB_pad + col0, full0 + 8 * s);
                     }
                 }
@@ -227,7 +259,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             uint32_t it = 0, tcount = 0;
             long long m_full = 0, m_empty = 0;
             const long long m_t0 = clock64();
-            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+            for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++tcount) {
                 const long long e0 = clock64();
                 mbar_wait(acc_empty, (tcount & 1u) ^ 1u);   // epilogue of the previous tile has drained TMEM
                 m_empty += clock64() - e0;
@@ -257,7 +289,10 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             tc_mma_i8(tmem + 64u * (pp + 4), ad, oz_smem_desc(st + S * OZ_A_TILE + 4 * OZ_B_TILE),
                                       IDESC_BASE | ((uint32_t)((nq - 4) * OZ_BN >> 3) << 17), acc);
                     }
-                    tc_commit(empty0 + 8 * s);
+                    if (CL == 2)
+                        tc_commit_mc(empty0 + 8 * s, (uint16_t)3);
+                    else
+                        tc_commit(empty0 + 8 * s);
                 }
                 tc_commit(acc_full);
             }
@@ -272,9 +307,9 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         const int quarter = warp & 3;
         uint32_t tcount = 0;
         long long c_wait = 0, c_ld = 0, c_upd = 0;
-        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++tcount) {
+        for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++tcount) {
             const int2 tt = p.tile_list[tile];
-            const int ti = tt.x, tj = tt.y;
+            const int ti = tt.x, tj = CL * tt.y + (int)crank;
             const int row = ti * OZ_BM + 32 * quarter + lane;
             const int col0 = tj * OZ_BN;
             // coalesced mapping of the C update: 16 consecutive threads cover the 128 bytes of one row of a 16-column chunk
@@ -364,6 +399,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (CL == 2) cluster_sync_all();   // no commit of mine may still be on its way to a peer that has exited
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -428,9 +464,11 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     // being equally long, in k-lockstep: if those tiles form a compact block of (row block, column block) pairs, each
     // operand block is fetched from HBM once per round and served to the other tiles from L2.  Bands of G row blocks,
     // column-major inside a band: a round covers ~G x (sm_count/G) tiles = G + sm_count/G distinct operand blocks.
+    const int CL = (ctx->oz_cluster == 2) ? 2 : 1;
+    const int pairs_n = (a.tiles_n + CL - 1) / CL;   // list entries per row block: column tiles (CL = 1) or pairs of them
     OzTileList* tl = nullptr;
     for (auto& l : w.lists)
-        if (l.tm == a.tiles_m && l.tn == a.tiles_n && l.lower == a.lower_only) tl = &l;
+        if (l.tm == a.tiles_m && l.tn == a.tiles_n && l.lower == a.lower_only && l.cl == CL) tl = &l;
     if (!tl) {
         tl = &w.lists[w.next_list];
         w.next_list = (w.next_list + 1) % 8;
@@ -438,14 +476,17 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
         const int G = 8;
         for (int b0 = 0; b0 < a.tiles_m; b0 += G) {
             const int b1 = b0 + G < a.tiles_m ? b0 + G : a.tiles_m;
-            const int tjmax = lower_only ? (2 * (b1 - 1) + 1 < a.tiles_n - 1 ? 2 * (b1 - 1) + 1 : a.tiles_n - 1) : a.tiles_n - 1;
-            for (int tj = 0; tj <= tjmax; ++tj)
+            // lower: row block ti owns column tiles 0 .. 2 ti + 1, i.e. pairs 0 .. ti
+            const int last = lower_only ? (CL == 2 ? b1 - 1 : 2 * (b1 - 1) + 1) : pairs_n - 1;
+            const int jmax = last < pairs_n - 1 ? last : pairs_n - 1;
+            for (int tj = 0; tj <= jmax; ++tj)
                 for (int ti = b0; ti < b1; ++ti)
-                    if (!lower_only || tj <= 2 * ti + 1) tl->host.push_back(make_int2(ti, tj));
+                    if (!lower_only || tj <= (CL == 2 ? ti : 2 * ti + 1)) tl->host.push_back(make_int2(ti, tj));
         }
         tl->tm = a.tiles_m;
         tl->tn = a.tiles_n;
         tl->lower = a.lower_only;
+        tl->cl = CL;
         tl->count = (int64_t)tl->host.size();
         // a list may still be in use by a kernel queued earlier on this stream: the copy is stream-ordered behind it
         RET_IF(ensure(ctx, tl->dev, tl->host.size() * sizeof(int2)));
@@ -460,12 +501,30 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     constexpr int smem_bytes = OZ_STAGES * S * (OZ_A_TILE + OZ_B_TILE) + 128 + (128 * 17 + 128) * 8 + 1024;
     static std::atomic<bool> attr{false};
     if (!attr) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr = true;
     }
-    const int nsm = persist_sms(ctx, st);
-    const int grid = (int)(tiles < nsm ? tiles : nsm);
-    oz_mma_kernel<S><<<grid, OZ_THREADS, smem_bytes, st>>>(mapA, mapB, a);
+    const int nsm = persist_sms(ctx);
+    if (CL == 2) {
+        const int ncl = nsm / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * (tiles < ncl ? tiles : ncl)));
+        cfg.blockDim = dim3(OZ_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, oz_mma_kernel<S, 2>, mapA, mapB, a));
+    } else {
+        const int grid = (int)(tiles < nsm ? tiles : nsm);
+        oz_mma_kernel<S, 1><<<grid, OZ_THREADS, smem_bytes, st>>>(mapA, mapB, a);
+    }
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return B2GP_OK;
