@@ -386,8 +386,8 @@ def main():
         # dominant kernel: oz_mma_kernel<8> (int8 tcgen05.mma into TMEM, TMA-fed).  Algorithmic work of the launch =
         # 36 digit-plane-pair int8 GEMMs of the 8192x8192 lower half at k = 8192; denominator = int8 dense tensor peak.
         "roofline": {"bound": "tensor", "achieved": int8_tops, "peak": int8_peak, "unit": "TOP/s (int8)", "frac": int8_tops / int8_peak,
-                     "traffic": traffic, "kernel": "oz_slice_kernel<8> + oz_mma_kernel<8> (UTCIMMA M128 N64 K32, TMEM accumulators, "
-                     "TMA 32B-swizzle stages; SYRK 8192x8192 k=8192 lower)", "int8_ops_per_launch": dom["int8_ops_per_launch"],
+                     "traffic": traffic, "kernel": "oz_slice_kernel<8> + oz_mma_kernel<8,2> (UTCIMMA M128 N<=256 K32 over stacked digit planes, TMEM "
+                     "accumulators, CTA-pair TMA multicast, 32B-swizzle stages; SYRK 8192x8192 k=8192 lower)", "int8_ops_per_launch": dom["int8_ops_per_launch"],
                      "ms_per_launch": oz["ms"], "peak_source": int8_src,
                      "fp64_equiv_tflops": oz["fp64_equiv_tflops"], "fp64_equiv_over_cublas_dgemm": oz["fp64_equiv_tflops"] / peak64,
                      "digit_planes": dom["planes"], "plane_pairs": dom["pairs"]},

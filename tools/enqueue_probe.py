@@ -10,22 +10,13 @@ rng = np.random.default_rng(0)
 N, P, d, S = 16384, 1024, 3, 16
 X = rng.uniform(0, 1, (N, d)); y = np.sin(3 * X[:, 0]) + 0.1 * rng.standard_normal(N); Xn = rng.uniform(0, 1, (P, d))
 theta = np.tile(np.array([0.3, 0.3, 0.3, 1.0, 0.1, 1.0]), (S, 1))
-import os
-for streams, lanes in ((4, 0), (4, 16), (4, 24), (4, 32), (8, 24), (8, 32), (6, 24), (4, 0)):
+for streams, thr in ((1, 1), (2, 1), (4, 0), (4, 1), (8, 1)):
     ctx.set_option("streams", streams)
-    try:
-        ctx.set_option("lanes", lanes)
-    except Exception as e:
-        print("lanes", lanes, "unsupported:", e, flush=True)
-        continue
+    ctx.set_option("enqueue_threads", thr)
     for rep in range(2):
         t0 = time.perf_counter()
         o = ctx.posterior("RBF", X, y, Xn, theta, want=("mean", "var"), timing=False)
         wall = (time.perf_counter() - t0) * 1e3
-    if lanes == 0 and streams == 4:
-        ref = o
-    else:
-        assert np.array_equal(o["mean"], ref["mean"]) and np.array_equal(o["var"], ref["var"]), "results differ"
     t = ctx.last_timing()
-    print("streams", streams, "lanes", lanes, "total_ms", round(t["total_ms"], 1), "per draw", round(t["total_ms"] / S, 2), "host_enqueue_ms",
-          round(t["host_enqueue_ms"], 1), "launches", t["launches"], "MAXCONN", os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), flush=True)
+    print("streams", streams, "threads", thr, "total_ms", round(t["total_ms"], 1), "per draw", round(t["total_ms"] / S, 2), "host_enqueue_ms",
+          round(t["host_enqueue_ms"], 1), "launches", t["launches"], flush=True)
