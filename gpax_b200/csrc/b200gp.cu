@@ -212,6 +212,11 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
         ctx->ozaki = (int)value;
         return B2GP_OK;
     }
+    if (strcmp(key, "trsm_strip") == 0) {
+        ARG_CHECK(ctx, value == 0 || value == 256 || value == 512 || value == 1024);
+        ctx->trsm_strip = (int)value;
+        return B2GP_OK;
+    }
     if (strcmp(key, "oz_cluster") == 0) {
         ARG_CHECK(ctx, value == 1 || value == 2);
         ctx->oz_cluster = (int)value;

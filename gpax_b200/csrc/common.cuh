@@ -55,6 +55,7 @@ struct b2gp_ctx {
     int enqueue_threads = 1;  // queue the draws of a multi-draw posterior from one host thread per slot
     int big_grid = 0;        // CTAs of the persistent kernels (0 = one per SM); fewer leaves SMs for other streams' small kernels
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
+    int trsm_strip = 256;  // widest factor solved by the one-launch strip kernel (0: recurse down to the 128 leaves)
     int oz_cluster = 2;  // 2: CTA pairs share the A digit planes by TMA multicast; 1: independent CTAs
     int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
     Slot slots[B2GP_MAX_STREAMS];

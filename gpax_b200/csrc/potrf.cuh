@@ -404,6 +404,149 @@ static inline int64_t split_point(int64_t n) {
     return h >= n ? n - (n > B2GP_LEAF ? B2GP_LEAF : 0) : h;
 }
 
+// ---------------------------------------------------------------------------------------------- strip solve
+// B (m x n) <- B L^{-T} for a narrow factor (n <= 512) in ONE launch: the rows of B are independent, so a CTA takes a
+// 32-row strip through the whole block forward substitution
+//     for each 128-column block j:   T = B_j - sum_{k < 128 j} X[:, k] L[j-block, k]^T ;   X_j = T Linv_j^T
+// with the same cp.async / DMMA tile loop as gemm_nt_kernel<32, 128, 1, 8, 3>, reading its own earlier results back
+// through L2.  The recursion it replaces issues 2^(log2(n/128)+1) - 1 dependent launches (7 for n = 512) of thin k = 128
+// GEMMs whose cost is all prologue and epilogue.
+struct TrsmStripArgs {
+    double* B;
+    int64_t ldb;
+    int m, n;
+    const double* L;
+    int64_t ldl;
+    const double* Linv;  // 128 x 128 inverted diagonal blocks, block 0 first
+};
+
+constexpr int TS_BM = 32, TS_BN = 128, TS_STAGES = 3, TS_THREADS = 256;
+constexpr int TS_STAGE_ELEMS = (TS_BM + TS_BN) * GEMM_LDS;
+constexpr int TS_SMEM = TS_STAGES * TS_STAGE_ELEMS * (int)sizeof(double);
+
+// acc (32 x 128 tile, warp w owns columns 16 w .. 16 w + 15) = A[row0.., 0..k) * Bop[0..brows, 0..k)^T
+template <bool ALIGNED>
+__device__ __forceinline__ void ts_tile_gemm(double (&acc)[4][2][2], double* smem, const double* A, int64_t lda, int a_rows, int row0,
+                                             const double* Bop, int64_t ldbop, int b_rows, int k, int tid) {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int KT = (k + GEMM_BK - 1) / GEMM_BK;
+#pragma unroll
+    for (int s = 0; s < TS_STAGES - 1; ++s) {
+        if (s < KT) {
+            double* As = smem + s * TS_STAGE_ELEMS;
+            load_slice<TS_BM, TS_THREADS, ALIGNED>(As, A, lda, a_rows, k, row0, s * GEMM_BK, tid);
+            load_slice<TS_BN, TS_THREADS, ALIGNED>(As + TS_BM * GEMM_LDS, Bop, ldbop, b_rows, k, 0, s * GEMM_BK, tid);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < KT; ++kt) {
+        cp_async_wait<TS_STAGES - 2>();
+        __syncthreads();
+        {
+            const int nk = kt + TS_STAGES - 1;
+            if (nk < KT) {
+                double* As = smem + (nk % TS_STAGES) * TS_STAGE_ELEMS;
+                load_slice<TS_BM, TS_THREADS, ALIGNED>(As, A, lda, a_rows, k, row0, nk * GEMM_BK, tid);
+                load_slice<TS_BN, TS_THREADS, ALIGNED>(As + TS_BM * GEMM_LDS, Bop, ldbop, b_rows, k, 0, nk * GEMM_BK, tid);
+            }
+            cp_async_commit();
+        }
+        const double* As = smem + (kt % TS_STAGES) * TS_STAGE_ELEMS + g * GEMM_LDS + t4;
+        const double* Bs = smem + (kt % TS_STAGES) * TS_STAGE_ELEMS + TS_BM * GEMM_LDS + (warp * 16 + g) * GEMM_LDS + t4;
+#pragma unroll
+        for (int kk = 0; kk < GEMM_BK / 4; ++kk) {
+            double a[4], b[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[i * 8 * GEMM_LDS + kk * 4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) b[j] = Bs[j * 8 * GEMM_LDS + kk * 4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // every thread is done with the stages (the next call refills them) and with its reads of A
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(TS_THREADS, 2) trsm_strip_kernel(const TrsmStripArgs p) {
+    extern __shared__ __align__(16) double ts_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int row0 = blockIdx.x * TS_BM;
+    const int nblk = (p.n + 127) / 128;
+    double acc[4][2][2];
+    for (int jb = 0; jb < nblk; ++jb) {
+        const int c0 = jb * 128;
+        const int cw = p.n - c0 < 128 ? p.n - c0 : 128;
+        if (jb > 0) {
+            // T = B_j - X[:, 0..c0) L[c0.., 0..c0)^T, written over B_j
+            ts_tile_gemm<ALIGNED>(acc, ts_smem, p.B, p.ldb, p.m, row0, p.L + (int64_t)c0 * p.ldl, p.ldl, cw, c0, tid);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = row0 + i * 8 + g;
+                if (r >= p.m) continue;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int c = warp * 16 + j * 8 + t4 * 2;
+                    double* dst = p.B + (int64_t)r * p.ldb + c0 + c;
+                    if (c < cw) dst[0] = -acc[i][j][0] + dst[0];
+                    if (c + 1 < cw) dst[1] = -acc[i][j][1] + dst[1];
+                }
+            }
+            __syncthreads();   // T complete (CTA-private rows) before it is read back as the A operand
+        }
+        // X_j = T Linv_j^T, in place: all of T is in flight / in shared memory before the first store (see ts_tile_gemm's tail)
+        ts_tile_gemm<ALIGNED>(acc, ts_smem, p.B + c0, p.ldb, p.m, row0, p.Linv + (int64_t)jb * 128 * 128, 128, cw, cw, tid);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = row0 + i * 8 + g;
+            if (r >= p.m) continue;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = warp * 16 + j * 8 + t4 * 2;
+                double* dst = p.B + (int64_t)r * p.ldb + c0 + c;
+                if (c < cw) dst[0] = acc[i][j][0];
+                if (c + 1 < cw) dst[1] = acc[i][j][1];
+            }
+        }
+        __syncthreads();       // X_j visible to this CTA's later loads
+    }
+}
+
+static int launch_trsm_strip(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t n,
+                             const double* Linv) {
+    TrsmStripArgs a;
+    a.B = B;
+    a.ldb = ldb;
+    a.m = (int)m;
+    a.n = (int)n;
+    a.L = L;
+    a.ldl = ldl;
+    a.Linv = Linv;
+    const bool aligned = ((ldb & 1) == 0) && ((ldl & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Linv) & 15) == 0);
+    static std::atomic<bool> attr{false};
+    if (!attr) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
+        attr = true;
+    }
+    const unsigned grid = (unsigned)ceil_div(m, TS_BM);
+    if (aligned)
+        trsm_strip_kernel<true><<<grid, TS_THREADS, TS_SMEM, st>>>(a);
+    else
+        trsm_strip_kernel<false><<<grid, TS_THREADS, TS_SMEM, st>>>(a);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return B2GP_OK;
+}
+
 // B (m x n, one right-hand side per row) <- B L^{-T}; L is n x n lower at `L`, its inverted diagonal
 // blocks at `Linv` (block b0 first).
 static int trsm_rec(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl,
@@ -413,6 +556,7 @@ static int trsm_rec(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int6
         // in place: C aliases A, one column tile
         return gemm_nt(ctx, st, m, n, n, 1.0, B, ldb, Linv, 128, 0.0, B, ldb, false);
     }
+    if (n <= ctx->trsm_strip) return launch_trsm_strip(ctx, st, B, ldb, m, L, ldl, n, Linv);
     const int64_t n1 = split_point(n), n2 = n - n1;
     RET_IF(trsm_rec(ctx, st, B, ldb, m, L, ldl, n1, Linv));
     RET_IF(gemm_nt(ctx, st, m, n2, n1, -1.0, B, ldb, L + n1 * ldl, ldl, 1.0, B + n1, ldb, false));

@@ -161,6 +161,27 @@ def test_potrf(ctx, n):
     np.testing.assert_array_equal(np.triu(L, 1), np.triu(A, 1))                # strict upper untouched
 
 
+@pytest.mark.parametrize("n,nrhs", [(129, 5), (256, 32), (300, 77), (511, 31), (512, 1025), (1000, 64), (2048, 300)])
+def test_trsm_strip_kernel_matches_recursion(ctx, n, nrhs):
+    """the one-launch strip solve (factors up to 512 wide, potrf.cuh) against the recursive GEMM formulation it replaces"""
+    rng = np.random.default_rng(7 * n + nrhs)
+    A = spd(rng, n)
+    B = rng.standard_normal((nrhs, n))
+    out = {}
+    try:
+        for strip in (0, 256, 512):
+            ctx.set_option("trsm_strip", strip)
+            L, info = ctx.potrf(A)
+            assert info == 0
+            out[strip] = (np.tril(L), ctx.trsm_lower(L, B))
+    finally:
+        ctx.set_option("trsm_strip", 256)
+    ref = sla.solve_triangular(out[0][0], B.T, lower=True).T
+    for strip in (256, 512):
+        np.testing.assert_allclose(out[strip][0], out[0][0], rtol=0, atol=1e-12 * np.abs(out[0][0]).max())
+        np.testing.assert_allclose(out[strip][1], ref, rtol=0, atol=1e-11 * np.abs(ref).max())
+
+
 def test_potrf_not_positive_definite(ctx):
     rng = np.random.default_rng(0)
     A = spd(rng, 200)
@@ -172,7 +193,7 @@ def test_potrf_not_positive_definite(ctx):
     assert ctx.potrf(A)[1] == 1
 
 
-@pytest.mark.parametrize("n,nrhs", [(1, 1), (100, 3), (128, 128), (300, 17), (640, 200), (1000, 1)])
+@pytest.mark.parametrize("n,nrhs", [(1, 1), (100, 3), (128, 128), (300, 17), (640, 200), (1000, 1), (512, 33), (1536, 1025)])
 def test_trsm(ctx, n, nrhs):
     rng = np.random.default_rng(n + nrhs)
     A = spd(rng, n)
