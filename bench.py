@@ -109,6 +109,8 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as td_
         torch.cuda.set_device(local)
+        # NCCL writes its banner / debug lines to stdout by default: keep stdout for the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td_.init_process_group("nccl", device_id=torch.device("cuda", local))
         td = td_
     return rank, world, local, td
