@@ -100,6 +100,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# stdout carries exactly ONE line, the JSON result: libraries that write to the C-level stdout (NCCL prints its version
+# banner there) are diverted to stderr for the life of the process and the result goes to the saved descriptor.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(text):
+    sys.stdout.flush()
+    os.write(_RESULT_FD, (text + "\n").encode())
+
+
 def dist_setup(n_gpus):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -109,8 +120,6 @@ def dist_setup(n_gpus):
         import torch
         import torch.distributed as td_
         torch.cuda.set_device(local)
-        # NCCL writes its banner / debug lines to stdout by default: keep stdout for the one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         td_.init_process_group("nccl", device_id=torch.device("cuda", local))
         td = td_
     return rank, world, local, td
@@ -251,7 +260,7 @@ def run_reference_arm(args, rank):
                                        "oracle.exact_posterior = NumPy restatement of gpax ExactGP.get_mvn_posterior "
                                        "(explicit inverse); gpax itself needs JAX, which is not installable here"},
             "e2e": {"value": val, "unit": "posteriors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 def main():
@@ -400,7 +409,7 @@ def main():
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if td is not None:
         td.destroy_process_group()
 
