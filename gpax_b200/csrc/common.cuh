@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -74,7 +75,11 @@ struct b2gp_ctx {
 static inline int set_err(b2gp_ctx* ctx, int code, const char* what, const char* detail, const char* file, int line) {
     char buf[512];
     snprintf(buf, sizeof buf, "%s: %s (%s:%d)", what, detail ? detail : "", file, line);
-    if (ctx) ctx->err = buf;
+    if (ctx) {
+        static std::mutex mu;  // draws of one call may be queued (and fail) on several host threads
+        std::lock_guard<std::mutex> lock(mu);
+        ctx->err = buf;
+    }
     return code;
 }
 
