@@ -12,7 +12,7 @@ import numpy as np
 
 from . import _ffi
 from .kernels import builtin_name, get_kernel
-from .utils import seed_from_key, split_in_batches
+from .utils import posterior_eps, split_in_batches, x64_enabled
 
 kernel_fn_type = Callable[[np.ndarray, np.ndarray, Dict[str, np.ndarray], np.ndarray], np.ndarray]
 
@@ -42,6 +42,10 @@ def _theta_rows(params: Dict[str, np.ndarray], d: int, batched: bool) -> np.ndar
     th[:, :d] = ell                       # scalar lengthscale broadcasts over the d features
     th[:, d], th[:, d + 1], th[:, d + 2] = scale, noise, period
     return th
+
+
+def _eps_dtype():
+    return np.float64 if x64_enabled() else np.float32
 
 
 class ExactGP:
@@ -202,7 +206,7 @@ class ExactGP:
                  **kwargs: float) -> Tuple[np.ndarray, np.ndarray]:
         """Prediction with a single sample of GP parameters (gp.py:279-293): (mean [P], samples [n, P])."""
         Xn = self._set_data(X_new)
-        eps = seed_from_key(rng_key).standard_normal((1, n, Xn.shape[0]))
+        eps = posterior_eps(rng_key, 1, n, Xn.shape[0], _eps_dtype(), per_draw_keys=False)
         if self._fused is None:
             mean, cov = self._posterior_callable(Xn, params, noiseless, **kwargs)
             Lc, info = self.ctx.potrf(cov)
@@ -232,7 +236,7 @@ class ExactGP:
             samples = self.get_samples(chain_dim=False)
         S = len(next(iter(samples.values())))
         P = X_new.shape[0]
-        eps = seed_from_key(rng_key).standard_normal((S, n, P))
+        eps = posterior_eps(rng_key, S, n, P, _eps_dtype())
         out = self._posterior_batched(X_new, samples, True, noiseless, ("mean",), eps=eps, **kwargs)
         y_means, y_sampled = out["mean"], out["y_sampled"]
         if filter_nans:                                     # gp.py:396-398

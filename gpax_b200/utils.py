@@ -5,17 +5,43 @@ restated on NumPy.  Nothing here is numerical work.
 import numpy as np
 
 
+_X64 = False
+
+
 def enable_x64():
-    """gpax/utils/utils.py:19-21.  The B200 path always computes in fp64; kept for drop-in use."""
-    return None
+    """gpax/utils/utils.py:19-21.  The B200 path always computes in fp64; what the switch changes here is what it
+    changes in the reference's random stream: `jax.random.normal` draws float64 variates from 64-bit words instead of
+    float32 ones from 32-bit words, so y_sampled for a given key follows the reference in either mode."""
+    global _X64
+    _X64 = True
+
+
+def x64_enabled() -> bool:
+    return _X64
 
 
 def get_keys(seed: int = 0):
-    """gpax/utils/utils.py:24-30: two keys for fit / predict.  Keys here are uint32[2] arrays used only
-    as seeds (JAX's threefry stream is not reproduced)."""
-    ss = np.random.SeedSequence(seed)
-    a, b = ss.spawn(2)
-    return a.generate_state(2).astype(np.uint32), b.generate_state(2).astype(np.uint32)
+    """gpax/utils/utils.py:24-30: `jax.random.split(jax.random.PRNGKey(seed))` -- the same two uint32[2] keys
+    (prng.py restates JAX's threefry key derivation)."""
+    from .prng import PRNGKey, split
+    k = split(PRNGKey(seed), 2)
+    return k[0], k[1]
+
+
+def posterior_eps(rng_key, num_draws, n, P, dtype=np.float32, per_draw_keys=True):
+    """Standard normals behind y_sampled, shape (num_draws, n, P), float64.
+
+    An int seed or a JAX-style uint32[2] key reproduces the reference's stream: one sub-key per hyper-parameter draw
+    (`jra.split(rng_key, num_samples)`, gp.py:391), `jax.random.normal(key, (n, P))` in the precision the reference
+    runs in (float32 unless `enable_x64()` was called, as there).  `per_draw_keys=False` is the
+    single-draw `_predict` (gp.py:279-293), which hands `rng_key` to the sampler as it is.  A numpy Generator (or
+    None) is this package's own extension and draws from that generator."""
+    if rng_key is None or isinstance(rng_key, np.random.Generator):
+        return seed_from_key(rng_key).standard_normal((num_draws, n, P))
+    from . import prng
+    if per_draw_keys:
+        return prng.mvn_eps(rng_key, num_draws, n, P, dtype)
+    return prng.normal(prng.as_key(rng_key), (n, P), dtype).astype(np.float64)[None]
 
 
 def seed_from_key(rng_key):

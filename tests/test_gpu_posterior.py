@@ -203,6 +203,34 @@ def test_predict_contract(gp, n, xdim):
     assert pm.shape == (20,) and ps.shape == (n, 20)
 
 
+def test_predict_samples_follow_the_reference_key_stream(gp):
+    """ExactGP.predict(rng_key, ...) draws what the reference draws for that key: one threefry sub-key per hyper-parameter
+    draw (gp.py:391), float32 normals (x64 off), y = mean + chol(cov) eps (gp.py:292) -- eps rebuilt here from the key"""
+    from gpax_b200 import prng
+    rng = np.random.default_rng(5)
+    N, P, S, n = 200, 30, 4, 3
+    X = rng.uniform(0, 1, (N, 2))
+    y = np.sin(4 * X[:, 0]) + X[:, 1] + 0.1 * rng.standard_normal(N)
+    Xt = rng.uniform(0, 1, (P, 2))
+    samples = {"k_length": np.exp(rng.normal(np.log(0.3), 0.1, (S, 2))), "k_scale": np.exp(rng.normal(0, 0.1, S)),
+               "noise": np.exp(rng.normal(np.log(0.1), 0.1, S))}
+    m = gp.ExactGP(2, "RBF")
+    m.X_train, m.y_train = X, y
+    key = prng.PRNGKey(11)
+    ymean, ysamp = m.predict(key, Xt, samples, n)
+    eps = prng.mvn_eps(key, S, n, P, np.float32)
+    ref_mean, _, ref_samp = oracle.predict_draws(X, y, Xt, samples, "RBF", n=n, eps=eps)
+    assert_close(ymean, ref_mean, RTOL)
+    assert_close(ysamp, ref_samp, 1e-6)
+    _, ysamp_int = m.predict(11, Xt, samples, n)                      # an int seed is PRNGKey(seed)
+    np.testing.assert_array_equal(ysamp_int, ysamp)
+    one = {k: v[1] for k, v in samples.items()}
+    pm, ps = m._predict(key, Xt, one, n)                              # single draw: the key itself (gp.py:292)
+    e1 = prng.normal(key, (n, P), np.float32).astype(np.float64)
+    rm, rc = oracle.exact_posterior(X, y, Xt, one, "RBF")
+    assert_close(ps, rm[None, :] + e1 @ np.linalg.cholesky(rc).T, 1e-6)
+
+
 def test_predict_negative_hyperparameters_tolerated(gp):
     """tests/test_gp.py:196-198 draws from N(0,1): about half are negative -> NaN draws, filter_nans drops them"""
     X, y = dummy()
