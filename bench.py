@@ -189,34 +189,40 @@ def measure_dominant_kernel(ctx, ffi):
 
 
 def cpu_baseline(budget_s=30.0):
-    """The oracle (port of the reference formulation, np.linalg.inv) on the host cores, bounded sample."""
+    """The oracle on the host cores, bounded samples.  `value` is the reference formulation (explicit inverse, 2 N^3:
+    what gpax's own CPU path does); `best_cpu_formulation` is the same posterior by Cholesky (N^3 / 3), reported so
+    that the GPU/CPU ratio is not inflated by the reference's choice of algorithm."""
     import oracle
     w = WORKLOAD
     cores = os.cpu_count()
     rng = np.random.default_rng(4)
     params = {"k_length": np.full(w["d"], w["ell"]), "k_scale": w["scale"], "noise": w["noise"]}
 
-    def run(N):
+    def run(N, fn):
         X = rng.uniform(0, 1, (N, w["d"]))
         y = rng.standard_normal(N)
         Xn = rng.uniform(0, 1, (w["P"], w["d"]))
         t0 = time.perf_counter()
-        oracle.exact_posterior(X, y, Xn, params, "RBF", jitter=w["jitter"])
+        fn(X, y, Xn, params, "RBF", jitter=w["jitter"])
         return time.perf_counter() - t0
-    run(1024)
-    t4 = run(4096)
-    est_full = t4 * (w["N"] / 4096) ** 3
-    if est_full <= budget_s * 1.5:
-        t = run(w["N"])
-        return {"value": 1.0 / t, "unit": "posteriors/s", "cores": cores, "kind": "port",
-                "sample": f"1 posterior at N={w['N']} P={w['P']} (oracle.exact_posterior, explicit inverse), {t:.1f} s"}
-    N = 4096
-    while N * 2 <= w["N"] and t4 * ((N * 2) / 4096) ** 3 <= budget_s:
-        N *= 2
-    t = run(N) if N != 4096 else t4
-    scaled = t * (w["N"] / N) ** 3
-    return {"value": 1.0 / scaled, "unit": "posteriors/s", "cores": cores, "kind": "port",
-            "sample": f"1 posterior at N={N} ({t:.1f} s) scaled by (16384/{N})^3 to N={w['N']} = {scaled:.1f} s"}
+
+    def sample(fn, what, budget):
+        run(1024, fn)
+        t4 = run(4096, fn)
+        if t4 * (w["N"] / 4096) ** 3 <= budget * 1.5:
+            t = run(w["N"], fn)
+            return {"value": 1.0 / t, "sample": f"1 posterior at N={w['N']} P={w['P']} ({what}), {t:.1f} s"}
+        N = 4096
+        while N * 2 <= w["N"] and t4 * ((N * 2) / 4096) ** 3 <= budget:
+            N *= 2
+        t = run(N, fn) if N != 4096 else t4
+        scaled = t * (w["N"] / N) ** 3
+        return {"value": 1.0 / scaled, "sample": f"1 posterior at N={N} ({t:.1f} s, {what}) scaled by (16384/{N})^3 to N={w['N']} = {scaled:.1f} s"}
+
+    ref = sample(oracle.exact_posterior, "oracle.exact_posterior, explicit inverse as gp.py:271", budget_s)
+    best = sample(oracle.exact_posterior_chol, "oracle.exact_posterior_chol, scipy cho_factor / cho_solve", budget_s / 2)
+    return {"value": ref["value"], "unit": "posteriors/s", "cores": cores, "kind": "port", "sample": ref["sample"],
+            "best_cpu_formulation": {"value": best["value"], "unit": "posteriors/s", "sample": best["sample"]}}
 
 
 def run_reference_arm(args, rank):
