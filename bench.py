@@ -30,7 +30,13 @@ import sys
 import threading
 import time
 
-import numpy as np
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  Rank 0 also times the CPU baseline / the reference arm, which are
+# to use all host cores, and OpenBLAS fixes its pool when NumPy is imported: lift the cap on rank 0 before that import.
+if os.environ.get("RANK", "0") == "0" and os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
+    os.environ["OPENBLAS_NUM_THREADS"] = str(os.cpu_count())
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -413,7 +419,7 @@ def main():
                           "frac": dom["dmma"]["fp64_equiv_tflops"] / peak64, "ms_per_launch": dom["dmma"]["ms"],
                           "kernel": "gemm_tma_kernel<3,2> (DMMA.8x8x4, TMA + mbarrier) + 64x64 tail launch", "peak_source": peak_src},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # a reported baseline of the N=1 line only
         line["cpu_baseline"] = cpu_baseline()
     emit(json.dumps(line))
     if td is not None:
