@@ -182,7 +182,7 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         for (int i = 0; i < B2GP_MAX_STREAMS; ++i) cudaEventDestroy(ex->slot_done[i]);
         cudaEventDestroy(ex->inputs_ready);
         free_buf(ex->theta1);
-
+        for (auto& b : ex->eb) free_buf(b);
         free_buf(ex->potrf_buf);
         for (auto& b : ex->gemm_buf) free_buf(b);
         for (void* p : ex->user_allocs) cudaFree(p);
@@ -208,7 +208,7 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
         return B2GP_OK;
     }
     if (strcmp(key, "ozaki") == 0) {
-        ARG_CHECK(ctx, value == 0 || value == 7 || value == 8);
+        ARG_CHECK(ctx, value == -1 || value == 0 || value == 6 || value == 7);
         ctx->ozaki = (int)value;
         return B2GP_OK;
     }
@@ -232,6 +232,11 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     }
     if (strcmp(key, "oz_min_tiles") == 0) {
         ctx->oz_min_tiles = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "oz_debug") == 0) {   // timing experiments only: 1 skips the C read-modify-write, 2 also the staging barriers
+        ARG_CHECK(ctx, value >= 0 && value <= 2);
+        ctx->oz_debug = (int)value;
         return B2GP_OK;
     }
     if (strcmp(key, "tma") == 0) {
@@ -578,31 +583,35 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     for (int q = 0; q < nslots; ++q)
         if (slot_stream(q) != st0) CUDA_TRY(ctx, cudaStreamWaitEvent(slot_stream(q), ex->inputs_ready, 0));
 
+    // host copy of theta: the accuracy-aware digit-plane count of the int8 path is chosen per draw (oz_auto_planes)
+    std::vector<double> htheta;
+    if (ctx->ozaki == -1) {
+        htheta.resize((size_t)S * nth);
+        if (dev) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(htheta.data(), dtheta, (size_t)S * nth * 8, cudaMemcpyDeviceToHost, st0));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+        } else {
+            memcpy(htheta.data(), theta, (size_t)S * nth * 8);
+        }
+    }
     const double noise_mult_new = noiseless ? 0.0 : 1.0;  // gp.py:260-261
     std::vector<StageEvents> sev;
     if (timing) sev.resize((size_t)S);
 
     // factor reuse (see Extra::fcache): same kind / N / d / jitter / theta / training inputs as the previous
     // single-draw host-pointer call -> skip the Gram build and the factorisation
+    // The cache is invalid for the whole duration of the call: any early return (allocation failure, launch error)
+    // leaves it so, and it is re-validated -- together with the factor's `info` -- only after the call's work has
+    // completed on the device (end of this function).
     bool reuse = false;
-    if (S == 1 && !dev) {
+    const bool cacheable = (S == 1 && !dev);
+    if (cacheable) {
         auto& fc = ex->fcache;
         reuse = fc.valid && fc.kind == kind && fc.N == N && fc.d == d && fc.jitter == jitter &&
                 memcmp(fc.theta.data(), theta, (size_t)nth * 8) == 0 && memcmp(fc.X.data(), Xtr, (size_t)N * d * 8) == 0;
-        if (!reuse) {
-            fc.valid = true;
-            fc.kind = kind;
-            fc.N = N;
-            fc.d = d;
-            fc.jitter = jitter;
-            fc.theta.assign(theta, theta + nth);
-            fc.X.assign(Xtr, Xtr + (size_t)N * d);
-        } else {
-            ex->cache_hits++;
-        }
-    } else {
-        ex->fcache.valid = false;
+        if (reuse) ex->cache_hits++;
     }
+    ex->fcache.valid = false;
 
     // One draw's whole pipeline, queued on its slot's stream.  Returns a B2GP_* code.
     auto enqueue_draw = [&](int64_t s) -> int {
@@ -618,6 +627,8 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
             for (int e = 0; e < 6; ++e) sev[s].e[e] = ex->pool.get();
             CUDA_TRY(ctx, cudaEventRecord(sev[s].e[0], st));
         }
+        // factorisation and P-side solve: 6 or 7 digit planes from the trace bound on cond(K); covariance / sampling: 7
+        sl.oz_planes = htheta.empty() ? 7 : oz_auto_planes((double)N, htheta[s * nth + d], htheta[s * nth + d + 1], jitter);
         if (!reuse) {
             // k_XX = kernel(X_train, X_train, params, noise, jitter)  (gp.py:269) -- lower triangle only
             RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXtr, N, d, th, 1.0, jitter, 1, 1, A, ldA));
@@ -645,6 +656,7 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
             ctx->launches++;
         }
         if (need_cov) {
+            sl.oz_planes = 7;
             // cov = k_pp - V^T V  (gp.py:267, 272), lower tiles then mirrored -> exactly symmetric
             double* C = want_cov ? dcov + s * P * P : (double*)sl.cov.p;
             const int64_t ldc = want_cov ? P : ldC;
@@ -720,8 +732,21 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     }
     CUDA_TRY(ctx, cudaEventRecord(ev_d, st0));
     RET_IF(tm.end(st0, nullptr));
+    for (int q = 0; q < B2GP_MAX_STREAMS; ++q) ctx->slots[q].oz_planes = 7;   // other entry points: the conservative count
     for (int64_t s = 0; s < S; ++s) info[s] = hinfo[s] != 0 ? hinfo[s] : -hinfo[S + s];
-    if (S == 1 && !dev) ex->fcache.info = hinfo[0];
+    if (cacheable) {
+        auto& fc = ex->fcache;
+        if (!reuse) {
+            fc.kind = kind;
+            fc.N = N;
+            fc.d = d;
+            fc.jitter = jitter;
+            fc.theta.assign(theta, theta + nth);
+            fc.X.assign(Xtr, Xtr + (size_t)N * d);
+            fc.info = hinfo[0];
+        }
+        fc.valid = true;
+    }
 
     b2gp_timing& t = ex->last;
     float ms = 0.f;
@@ -1338,10 +1363,10 @@ extern "C" int b2gp_debug_leaf(b2gp_ctx* ctx, int n, double* A_dev, int64_t lda,
     int* dinfo = (int*)ctx->d_info.p;
     long long* dprof = (long long*)((char*)ctx->d_info.p + 64);
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_info.p, 0, 64 + 128 * 8, st));
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
-        attr = true;
+        attr.done(ctx->device);
     }
     potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, st>>>(A_dev, lda, n, linv_dev, dinfo, 0, dprof);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -1390,10 +1415,10 @@ extern "C" int b2gp_debug_ozaki(b2gp_ctx* ctx, int S, int64_t m, int64_t n, int6
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->slots[0].oz.prof.p, 0, 148 * 8 * 8, st));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
     int rc;
-    if (S == 7)
-        rc = ozaki_gemm_nt<7>(ctx, st, ctx->slots[0].oz, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower != 0);
+    if (S == 6)
+        rc = ozaki_gemm_nt<6>(ctx, st, ctx->slots[0].oz, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower != 0);
     else
-        rc = ozaki_gemm_nt<8>(ctx, st, ctx->slots[0].oz, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower != 0);
+        rc = ozaki_gemm_nt<7>(ctx, st, ctx->slots[0].oz, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower != 0);
     RET_IF(rc);
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
     CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_b));

@@ -43,6 +43,7 @@ struct Slot {
     DevBuf LinvC;  // inverted diagonal blocks of chol(cov)
     DevBuf misc;   // small scratch
     OzWork oz;
+    int oz_planes = 7;  // digit planes of the int8 path for the work queued on this slot when ctx->ozaki == -1 (auto)
     cudaEvent_t ev[8];
 };
 
@@ -58,7 +59,10 @@ struct b2gp_ctx {
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
     int trsm_strip = 256;  // widest factor solved by the one-launch strip kernel (0: recurse down to the 128 leaves)
     int oz_cluster = 2;  // 2: CTA pairs share the A digit planes by TMA multicast; 1: independent CTAs
-    int ozaki = 8;    // 0: fp64 DMMA only; 7 / 8: large rank-k updates through the int8 tcgen05 path with that many digit planes
+    int oz_debug = 0;  // see OzArgs::debug (0 in production)
+    // 0: fp64 DMMA only; 6 / 7: large rank-k updates through the int8 tcgen05 path with that many base-256 digit planes
+    // (46 / 54 bits per operand); -1: 6 or 7 per factorisation from a bound on cond(K), see oz_auto_planes()
+    int ozaki = -1;
     Slot slots[B2GP_MAX_STREAMS];
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_a = nullptr, ev_b = nullptr;
     // staging for host-pointer entry points
@@ -119,10 +123,35 @@ static inline int ensure(b2gp_ctx* ctx, DevBuf& b, size_t bytes) {
     return B2GP_OK;
 }
 
+// cudaFuncSetAttribute is per device: a process may hold contexts on several devices (Context(device=1) next to
+// the default one), so the "already opted in to large dynamic shared memory" memo is a bit per device.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask{0};
+    bool need(int dev) const { return ((mask.load(std::memory_order_acquire) >> (dev & 63)) & 1ull) == 0; }
+    void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+
 static inline Slot* slot_of(b2gp_ctx* ctx, cudaStream_t st) {
     for (int i = 0; i < B2GP_MAX_STREAMS; ++i)
         if (ctx->slots[i].stream == st) return &ctx->slots[i];
     return nullptr;
+}
+
+// digit planes for the int8 GEMMs queued on stream `st`
+static inline int oz_planes_for(b2gp_ctx* ctx, cudaStream_t st) {
+    if (ctx->ozaki > 0) return ctx->ozaki;
+    Slot* sl = slot_of(ctx, st);
+    return sl ? sl->oz_planes : 7;
+}
+
+// Accuracy-aware plane count: the error the digit-plane GEMMs add to a posterior grows like
+// cond(K) * 1.3e-16 with 46-bit operands (6 planes) and cond(K) * 3e-18 with 54-bit ones (7 planes); against the 1e-9
+// parity bar 6 planes are safe while cond(K) <= 1e6.  cond(K) is bounded from the trace: lambda_max <= N k_scale +
+// sigma^2 + jitter, lambda_min >= sigma^2 + jitter  (K = k(X, X) + (sigma^2 + jitter) I, k(x, x) = k_scale).
+static inline int oz_auto_planes(double n, double k_scale, double noise, double jitter) {
+    const double floor_ = noise + jitter;
+    if (!(floor_ > 0.0) || !(k_scale > 0.0)) return 7;
+    return (n * k_scale + floor_) / floor_ <= 1e6 ? 6 : 7;
 }
 
 // CTAs a persistent (one CTA per SM) kernel should launch

@@ -210,10 +210,10 @@ static int launch_gemm_cfg(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     if (grid <= 0) return B2GP_OK;
     auto kern = aligned ? gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, true, MINB>
                         : gemm_nt_kernel<BM, BN, WARPS_M, WARPS_N, STAGES, false, MINB>;
-    static std::atomic<bool> attr_set[2];  // zero-initialised
-    if (!attr_set[aligned ? 1 : 0]) {
+    static PerDeviceOnce attr_set[2];
+    if (attr_set[aligned ? 1 : 0].need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr_set[aligned ? 1 : 0] = true;
+        attr_set[aligned ? 1 : 0].done(ctx->device);
     }
     kern<<<(unsigned)grid, WARPS_M * WARPS_N * 32, smem_bytes, st>>>(a);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -249,7 +249,7 @@ static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t
     // to the int8 tcgen05 path when it is enabled: measured 64 TFLOP/s-equivalent with 8 digit planes against
     // 35 for DMMA (ozaki.cuh).  It needs beta == 1, k within the int32 accumulation bound, enough 128x64 tiles to
     // fill the machine twice, and operands distinct from C (the in-place solve keeps the DMMA kernel).
-    if (ctx->ozaki && beta == 1.0 && k >= 512 && k <= 32768 && C != A && C != B) {
+    if (ctx->ozaki && beta == 1.0 && k >= 512 && C != A && C != B) {
         const int64_t tm = ceil_div(m, 128), tn = ceil_div(n, 64);
         const int64_t toz = lower_only ? tm * (tm + 1) : tm * tn;
         if (toz >= ctx->oz_min_tiles) {

@@ -236,10 +236,10 @@ static int launch_gemm_tma(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
     a.tiles_n = (a.n + TG_BN - 1) / TG_BN;
     const int64_t tiles = a.lower_only ? (int64_t)a.tiles_m * (a.tiles_m + 1) / 2 : (int64_t)a.tiles_m * a.tiles_n;
     if (tiles <= 0) return B2GP_OK;
-    static std::atomic<bool> attr{false};
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(gemm_tma_kernel<STAGES, KSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr = true;
+        attr.done(ctx->device);
     }
     // Wave quantisation: with T tiles on S SMs the persistent kernel takes ceil(T/S) tile-times.  The T mod S tiles
     // of the last, partial wave are handed to a follow-up launch as 64x64 quarters (2 CTAs/SM): a quarter of the
@@ -259,10 +259,10 @@ static int launch_gemm_tma(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
         t.tiles_n = (a.n + 63) / 64;
         constexpr int tail_smem = 4 * (64 + 64) * GEMM_LDS * (int)sizeof(double);
         auto kern = gemm_nt_kernel<64, 64, 2, 4, 4, true, 2>;
-        static std::atomic<bool> tattr{false};
-        if (!tattr) {
+        static PerDeviceOnce tattr;
+        if (tattr.need(ctx->device)) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tail_smem));
-            tattr = true;
+            tattr.done(ctx->device);
         }
         kern<<<(unsigned)(4 * (tiles - main_tiles)), 256, tail_smem, st>>>(t);
         CUDA_TRY(ctx, cudaGetLastError());

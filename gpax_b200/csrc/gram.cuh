@@ -359,10 +359,10 @@ static int launch_gram(b2gp_ctx* ctx, cudaStream_t st, int kind, const double* X
     a.K = K;
     a.ldk = ldk;
     const size_t smem = (size_t)(GRAM_BM * d + GRAM_BM + d * GRAM_BN + GRAM_BN + d) * sizeof(double);
-    static std::atomic<bool> attr{false};
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-        attr = true;
+        attr.done(ctx->device);
     }
     dim3 grid((unsigned)ceil_div(m, GRAM_BN), (unsigned)ceil_div(n, GRAM_BM));
     bool done = false;

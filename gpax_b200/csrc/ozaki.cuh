@@ -2,14 +2,18 @@
 //
 // sm_100a has no fp64 tcgen05.mma; what it has is kind::i8 with exact int32 accumulation in TMEM at ~16x the
 // DMMA rate.  C[m,n] += alpha * A[m,k] B[n,k]^T is evaluated as follows.
-//   1. slice (oz_slice_kernel): every row of A (and B) is scaled by a power of two 2^-e_i so that |a| < 1 and cut
-//      into S signed base-128 digits d_1..d_S in [-64, 64] (d_1 carries 6 bits, the others 7):
-//         a = 2^e_i * sum_p d_p 2^-w(p),   w(p) = 6 + 7 (p-1)          (exact up to 2^-(6+7(S-1)) ~ 2^-55 for S = 8)
+//   1. slice (oz_slice_kernel): every row of A (and B) is scaled by a power of two 2^-e_i so that |a| < 1, rounded ONCE
+//      to the integer I = rint(a 2^(8S-2-e_i)) (|I| <= 2^(8S-2)) and cut into S base-256 digits in two's-complement
+//      style, lowest first: d = signed low byte of I in [-128, 127], I <- (I - d) >> 8; the leading digit is what is left
+//      (6 bits + a carry).  Full-range int8 digits: 8 bits per plane instead of the 7 of a round-to-nearest base-128 split,
+//      so S = 7 planes carry 54 bits (what 8 planes did before) and 28 instead of 36 products; S = 6 carry 46 bits.
+//         a = 2^e_i * sum_q d_q 2^-w(q),   w(q) = 6 + 8 q,  q = 0 .. S-1   (exact to half a unit of the last digit)
 //      The digits are stored as S int8 planes [S][rows][k], K-major.
-//   2. products (oz_mma_kernel): A_p B_q^T is an int8 GEMM; its int32 result is EXACT (|d d'| <= 2^12, k <= 2^16).
-//      Its weight 2^-(12 + 7 (p+q-2)) depends on t = p+q-2 only, so all pairs of one weight class accumulate into the
+//   2. products (oz_mma_kernel): A_p B_q^T is an int8 GEMM; its int32 result is EXACT (|d d'| <= 2^14, at most S pairs
+//      per accumulator, k <= OZ_K_MAX = 16384 per launch: 7 * 2^14 * 2^14 < 2^31; longer k is split by the dispatcher).
+//      Its weight 2^-(12 + 8 (p+q)) depends on t = p+q only, so all pairs of one weight class accumulate into the
 //      same TMEM accumulator.  Classes t >= S are below the target precision and are dropped: S(S+1)/2 products.
-//   3. recombine (epilogue of the same kernel): acc = sum_t 2^-(12+7t) D_t in fp64, smallest class first, and
+//   3. recombine (epilogue of the same kernel): acc = sum_t 2^-(12+8t) D_t in fp64, smallest class first, and
 //      C[i,j] += alpha * 2^(e_i + f_j) * acc.
 // Kernel organisation (one CTA per SM, persistent):
 //   * output tile 128 x 64: S accumulators of 64 TMEM columns = 512 columns for S = 8 (all of TMEM);
@@ -29,6 +33,7 @@
 
 constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32, OZ_STAGES = 4;   // 32-byte k-blocks (one MMA K step), 4 stages in flight
 constexpr int OZ_THREADS = 192;
+constexpr int OZ_K_MAX = 16384;           // int32 accumulation bound of one launch (see above)
 constexpr int OZ_A_TILE = OZ_BM * OZ_KB;  // 4096 B
 constexpr int OZ_B_TILE = OZ_BN * OZ_KB;  // 2048 B
 
@@ -67,8 +72,10 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
         mx = red[0];
         for (int w = 1; w < 8; ++w) mx = fmax(mx, red[w]);
         if (mx > 0.0 && mx < 1e300) frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)
+        if (e < -900) e = -900;                      // 2^(8S-2-e) below must stay finite
         if (tid == 0) scale[row] = ldexp(1.0, e);
     }
+    const double up = ldexp(1.0, 8 * S - 2 - e);     // exact power of two: a * up is the exact scaling
     // 4 consecutive k per thread -> one 32-bit store per plane
     for (int k4 = tid * 4; k4 < kpad; k4 += 1024) {
         int packed[S];
@@ -77,13 +84,14 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int kk = k4 + j;
-            double v = (row < rows && kk < k) ? ldexp(A[(int64_t)row * lda + kk], 6 - e) : 0.0;
+            long long I = (row < rows && kk < k) ? __double2ll_rn(A[(int64_t)row * lda + kk] * up) : 0ll;
 #pragma unroll
-            for (int p = 0; p < S; ++p) {
-                const double d = rint(v);
-                packed[p] |= ((int)d & 0xff) << (8 * j);
-                v = (v - d) * 128.0;
+            for (int p = S - 1; p > 0; --p) {
+                const int d = (int)(signed char)(I & 0xff);          // signed low byte
+                packed[p] |= (d & 0xff) << (8 * j);
+                I = (I - d) >> 8;
             }
+            packed[0] |= ((int)I & 0xff) << (8 * j);
         }
 #pragma unroll
         for (int p = 0; p < S; ++p)
@@ -352,7 +360,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 for (int nb = 0; nb < 2 * S; ++nb) {
                     const int t = S - 1 - (nb >> 1), h = nb & 1;
                     if (nb + 1 < 2 * S) tc_ld32(trow + 64u * (S - 1 - ((nb + 1) >> 1)) + 32u * ((nb + 1) & 1), v[(nb + 1) & 1]);
-                    const double w = __longlong_as_double((long long)(1023 - (12 + 7 * t)) << 52);
+                    const double w = __longlong_as_double((long long)(1023 - (12 + 8 * t)) << 52);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) acc[32 * h + j] = fma(i32_to_f64(v[nb & 1][j]), w, acc[32 * h + j]);
                     if (nb + 1 < 2 * S) tc_wait_ld32(v[(nb + 1) & 1]);
@@ -423,7 +431,7 @@ template <int S>
 static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                          int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
     if (m <= 0 || n <= 0 || k <= 0) return B2GP_OK;
-    if (k > 32768) return B2GP_ERR_UNSUPPORTED;  // int32 accumulation bound: S * k * 2^12 < 2^31
+    if (k > OZ_K_MAX) return B2GP_ERR_UNSUPPORTED;  // int32 accumulation bound (the dispatcher splits longer k)
     const int64_t kpad = round_up(k, OZ_KB);
     const int64_t ra = round_up(m, 128), rb = round_up(n, 128);
     const bool same = (A == B && lda == ldb && m == n);
@@ -497,13 +505,13 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     a.tile_list = (const int2*)tl->dev.p;
     a.prof = nullptr;
     if (w.prof.p) a.prof = (long long*)w.prof.p;
-    a.debug = getenv("B2GP_OZ_DEBUG") ? atoi(getenv("B2GP_OZ_DEBUG")) : 0;
+    a.debug = ctx->oz_debug;
     constexpr int smem_bytes = OZ_STAGES * S * (OZ_A_TILE + OZ_B_TILE) + 128 + (128 * 17 + 128) * 8 + 1024;
-    static std::atomic<bool> attr{false};
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        attr = true;
+        attr.done(ctx->device);
     }
     const int nsm = persist_sms(ctx);
     if (CL == 2) {
@@ -534,6 +542,15 @@ static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, 
                           const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
     Slot* sl = slot_of(ctx, st);
     OzWork* w = sl ? &sl->oz : &ctx->slots[0].oz;
-    if (ctx->ozaki == 7) return ozaki_gemm_nt<7>(ctx, st, *w, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
-    return ozaki_gemm_nt<8>(ctx, st, *w, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
+    const int planes = oz_planes_for(ctx, st);
+    for (int64_t k0 = 0; k0 < k; k0 += OZ_K_MAX) {
+        const int64_t kc = k - k0 < OZ_K_MAX ? k - k0 : OZ_K_MAX;
+        int rc;
+        if (planes == 6)
+            rc = ozaki_gemm_nt<6>(ctx, st, *w, m, n, kc, alpha, A + k0, lda, B + k0, ldb, C, ldc, lower_only);
+        else
+            rc = ozaki_gemm_nt<7>(ctx, st, *w, m, n, kc, alpha, A + k0, lda, B + k0, ldb, C, ldc, lower_only);
+        if (rc != B2GP_OK) return rc;
+    }
+    return B2GP_OK;
 }

@@ -387,10 +387,10 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int n, double* __restrict
 
 static int potrf_diag(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int n, double* Linv_blk, int* info,
                       int index_base) {
-    static std::atomic<bool> attr{false};
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PD_SMEM));
-        attr = true;
+        attr.done(ctx->device);
     }
     potrf_diag_kernel<<<1, PD_THREADS, PD_SMEM, st>>>(A, lda, n, Linv_blk, info, index_base, nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -531,11 +531,11 @@ static int launch_trsm_strip(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t 
     a.Linv = Linv;
     const bool aligned = ((ldb & 1) == 0) && ((ldl & 1) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && ((reinterpret_cast<uintptr_t>(Linv) & 15) == 0);
-    static std::atomic<bool> attr{false};
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
         CUDA_TRY(ctx, cudaFuncSetAttribute(trsm_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM));
-        attr = true;
+        attr.done(ctx->device);
     }
     const unsigned grid = (unsigned)ceil_div(m, TS_BM);
     if (aligned)

@@ -270,8 +270,9 @@ class ExactGP:
     def fit(self, rng_key, X, y, num_warmup: int = 2000, num_samples: int = 2000, num_chains: int = 1,
             chain_method: str = "sequential", progress_bar: bool = True, print_summary: bool = True,
             device=None, rng_key_predict=None, **kwargs: float) -> None:
-        """gp.py:166-220.  HMC/NUTS over the hyper-parameters needs NumPyro in the reference; this build
-        ships the predict path (SURVEY.md section 8f-1 lists the fit path as the next row)."""
+        """gp.py:166-220.  The reference runs NumPyro's NUTS over the hyper-parameters; here a host-side NUTS
+        (gpax_b200/inference.py) samples the same posterior with the log marginal likelihood and its gradient
+        evaluated on the GPU (b2gp_mll), LogNormal(0, 1) priors by default (gp.py:222-247)."""
         from .inference import fit_exact_gp
         X, y = self._set_data(X, y)
         self.X_train, self.y_train = X, y

@@ -79,7 +79,8 @@ int  b2gp_version(void);
 int  b2gp_ctx_create(int device, b2gp_ctx** out);
 int  b2gp_ctx_destroy(b2gp_ctx* ctx);
 const char* b2gp_last_error(const b2gp_ctx* ctx);
-/* options: "streams" (draws in flight, 1..4, default 2), "leaf" ignored for now */
+/* options: "streams" (draws in flight, 1..8, default 2); "ozaki" (0: fp64 DMMA only, 7 / 8: int8 tcgen05 digit planes,
+ * -1: chosen per call from a bound on cond(K)); the full table is in INTEGRATION.md */
 int  b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value);
 int  b2gp_device_info(b2gp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* mem_bytes);
 /* device timing of the most recent entry-point call on this ctx (every call records total_ms) */

@@ -96,8 +96,9 @@ def test_many_draws_stream_through_few_workspaces(ctx):
 
 def test_int8_tcgen05_path_matches_fp64_dmma_path(ctx):
     """N = 8192 (large enough for the int8 digit-plane kernel to take the trailing updates): the posterior through the
-    tcgen05 path with 8 planes agrees with the all-fp64 DMMA path to the parity bar (1e-9, scale-relative) at
-    cond(K) ~ 1e5, and so does 7 planes to 1e-7; the factor itself agrees to 1e-12 of its scale."""
+    tcgen05 path with 7 base-256 planes agrees with the all-fp64 DMMA path to the parity bar (1e-9, scale-relative) at
+    cond(K) ~ 1e5, and so does 6 planes to 1e-7; the factor itself agrees to 1e-12 of its scale.  (The comparison
+    with the oracle at this size and at N = 16384 is tests/test_gpu_baseline_sizes.py.)"""
     import ctypes as C
     from gpax_b200 import _ffi
     N, d, P = 8192, 2, 200
@@ -107,14 +108,14 @@ def test_int8_tcgen05_path_matches_fp64_dmma_path(ctx):
     Xn = rng.uniform(0, 1, (P, d))
     theta = np.array([[0.25, 0.3, 1.0, 1e-3, 1.0]])       # noise 1e-3 -> cond(K) ~ N * scale / noise ~ 1e5 .. 1e6 effective
     res = {}
-    for planes in (0, 8, 7):
+    for planes in (0, 7, 6):
         ctx.set_option("ozaki", planes)
         ctx.set_option("drop_factor_cache", 1)
         res[planes] = ctx.posterior("Matern", X, y, Xn, theta, want=("mean", "var"))
         assert res[planes]["info"][0] == 0
-    ctx.set_option("ozaki", 8)
+    ctx.set_option("ozaki", -1)
     ref = res[0]
-    for planes, tol in ((8, 1e-9), (7, 1e-7)):
+    for planes, tol in ((7, 1e-9), (6, 1e-7)):
         for k in ("mean", "var"):
             err = np.abs(res[planes][k] - ref[k]).max() / np.abs(ref[k]).max()
             print(f"planes={planes} {k}: max scaled deviation from the fp64 DMMA path {err:.2e}")
@@ -123,7 +124,7 @@ def test_int8_tcgen05_path_matches_fp64_dmma_path(ctx):
     dX = ctx.to_device(X)
     ell = np.array([0.25, 0.3])
     Ls = {}
-    for planes in (0, 8):
+    for planes in (0, 7):
         ctx.set_option("ozaki", planes)
         K = ctx.alloc((N, N))
         ctx._check(ctx.lib.b2gp_gram(ctx.h, 1, dX.ptr, N, dX.ptr, N, d, _ffi._ptr(ell), 1.0, 1.0, 1e-3 + 1e-6, 1, K.ptr, N,
@@ -133,9 +134,9 @@ def test_int8_tcgen05_path_matches_fp64_dmma_path(ctx):
         assert info.value == 0
         Ls[planes] = _download_rows(ctx, K, N, N - 64, 64)      # the last 64 rows depend on every update
         K.free()
-    ctx.set_option("ozaki", 8)
+    ctx.set_option("ozaki", -1)
     mask = np.tril(np.ones((N, N), bool))[N - 64:]
-    dev = np.abs(Ls[8] - Ls[0])[mask].max() / np.abs(Ls[0][mask]).max()
+    dev = np.abs(Ls[7] - Ls[0])[mask].max() / np.abs(Ls[0][mask]).max()
     print(f"factor rows {N-64}..{N}: max scaled deviation {dev:.2e}")
     assert dev <= 1e-12
     dX.free()
