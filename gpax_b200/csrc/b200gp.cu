@@ -160,6 +160,7 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         free_buf(s.cov);
         free_buf(s.LinvC);
         free_buf(s.misc);
+        free_buf(s.panelU);
         free_buf(s.oz.planesA);
         free_buf(s.oz.planesB);
         free_buf(s.oz.scaleA);
@@ -232,6 +233,17 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
     }
     if (strcmp(key, "oz_min_tiles") == 0) {
         ctx->oz_min_tiles = (int)value;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "panel") == 0) {   // diagonal-block width of the tall-panel factorisation; 0 = recursive scheme only
+        ARG_CHECK(ctx, value == 0 || value == 128 || value == 256 || value == 512 || value == 1024);
+        ctx->panel = (int)value;
+        extra_of(ctx)->fcache.valid = false;
+        return B2GP_OK;
+    }
+    if (strcmp(key, "tall_min") == 0) {
+        ARG_CHECK(ctx, value >= 256);
+        ctx->tall_min = (int)value;
         return B2GP_OK;
     }
     if (strcmp(key, "oz_debug") == 0) {   // timing experiments only: 1 skips the C read-modify-write, 2 also the staging barriers
@@ -407,7 +419,7 @@ extern "C" int b2gp_potrf(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, int*
     RET_IF(ensure(ctx, ctx->last_linv, (size_t)linv_bytes(n)));
     RET_IF(ensure(ctx, ctx->d_info, 64));
     CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_info.p, 0, 8, st));
-    RET_IF(potrf_rec(ctx, st, dA, ld, n, (double*)ctx->last_linv.p, (int*)ctx->d_info.p, 0));
+    RET_IF(potrf_auto(ctx, st, dA, ld, n, 0, (double*)ctx->last_linv.p, (int*)ctx->d_info.p));
     ctx->last_n = n;
     if (!dev) {
         // the strict upper triangle of the caller's array is documented as untouched: stage the factor on the
@@ -567,12 +579,13 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, (size_t)2 * S * sizeof(int), st0));
 
     // ---- per-slot workspaces
+    // the right-hand-side rows [k_pX; y^T] live directly under k_XX in the slot's matrix (potrf_tall solves them with the
+    // factorisation's own panel GEMMs)
     const int64_t ldA = round_up(N, 8), ldV = ldA, ldC = round_up(P, 8);
     const bool need_cov = want_cov || want_samp;
     for (int q = 0; q < nslots; ++q) {
         Slot& sl = ctx->slots[q];
-        RET_IF(ensure(ctx, sl.A, (size_t)N * ldA * 8));
-        RET_IF(ensure(ctx, sl.Vt, (size_t)(P + 1) * ldV * 8));
+        RET_IF(ensure(ctx, sl.A, (size_t)(N + P + 1) * ldA * 8));
         RET_IF(ensure(ctx, sl.Linv, (size_t)linv_bytes(N)));
         if (need_cov) RET_IF(ensure(ctx, sl.cov, (size_t)P * ldC * 8));
         if (want_samp) RET_IF(ensure(ctx, sl.LinvC, (size_t)linv_bytes(P)));
@@ -618,9 +631,10 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
         Slot& sl = ctx->slots[s % nslots];
         cudaStream_t st = slot_stream((int)(s % nslots));
         double* A = (double*)sl.A.p;
-        double* Vt = (double*)sl.Vt.p;
+        double* Vt = A + N * ldA;
         double* Linv = (double*)sl.Linv.p;
         const double* th = dtheta + s * nth;
+        const bool fused_solve = !reuse && use_tall(ctx, N);   // the P-side solve rides along with the factorisation
         int* inf = dinfo + s;
         int* inf2 = dinfo + S + s;
         if (timing) {
@@ -629,23 +643,31 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
         }
         // factorisation and P-side solve: 6 or 7 digit planes from the trace bound on cond(K); covariance / sampling: 7
         sl.oz_planes = htheta.empty() ? 7 : oz_auto_planes((double)N, htheta[s * nth + d], htheta[s * nth + d + 1], jitter);
+        auto rhs_rows = [&]() -> int {
+            // k_pX = kernel(X_new, X_train, params, jitter=0.0)  (gp.py:268); same-shape inputs add 0 there
+            RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXtr, N, d, th, 0.0, 0.0, 0, 0, Vt, ldV));
+            CUDA_TRY(ctx, cudaMemcpyAsync(Vt + P * ldV, dy + (yres_stride ? s * yres_stride : 0), (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+            return B2GP_OK;
+        };
         if (!reuse) {
             // k_XX = kernel(X_train, X_train, params, noise, jitter)  (gp.py:269) -- lower triangle only
             RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXtr, N, d, th, 1.0, jitter, 1, 1, A, ldA));
+            if (fused_solve) RET_IF(rhs_rows());
             if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
-            // factor instead of jnp.linalg.inv (gp.py:271)
-            RET_IF(potrf_rec(ctx, st, A, ldA, N, Linv, inf, 0));
+            // factor instead of jnp.linalg.inv (gp.py:271); with the tall-panel scheme also [V^T; w^T] = [k_pX; y^T] L^{-T}
+            if (fused_solve)
+                RET_IF(potrf_tall(ctx, st, sl, A, ldA, N, P + 1, Linv, inf, 0));
+            else
+                RET_IF(potrf_rec(ctx, st, A, ldA, N, Linv, inf, 0));
         } else {
             if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
             CUDA_TRY(ctx, cudaMemcpyAsync(inf, &ex->fcache.info, sizeof(int), cudaMemcpyHostToDevice, st));
         }
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[2], st));
-        // k_pX = kernel(X_new, X_train, params, jitter=0.0)  (gp.py:268); same-shape inputs add 0 there
-        RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXtr, N, d, th, 0.0, 0.0, 0, 0, Vt, ldV));
-        CUDA_TRY(ctx, cudaMemcpyAsync(Vt + P * ldV, dy + (yres_stride ? s * yres_stride : 0), (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
+        if (!fused_solve) RET_IF(rhs_rows());
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[3], st));
         // [V^T; w^T] = [k_pX; y^T] L^{-T}
-        RET_IF(trsm_rec(ctx, st, Vt, ldV, P + 1, A, ldA, N, Linv));
+        if (!fused_solve) RET_IF(trsm_rec(ctx, st, Vt, ldV, P + 1, A, ldA, N, Linv));
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[4], st));
         // mean / var
         double* mean_s = want_mean ? dmean + s * P : (double*)sl.misc.p;

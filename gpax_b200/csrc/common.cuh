@@ -20,6 +20,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+#define OZ_LISTS 192
 // scratch of the int8-split (Ozaki) GEMM path, one per stream: digit planes, row scales, tile list
 struct OzTileList {
     int tm = -1, tn = -1, lower = -1, cl = -1;
@@ -29,7 +30,7 @@ struct OzTileList {
 };
 struct OzWork {
     DevBuf planesA, planesB, scaleA, scaleB, prof;
-    OzTileList lists[8];            // the few (tiles_m, tiles_n, lower) shapes one factorisation cycles through
+    OzTileList lists[OZ_LISTS];     // the (tiles_m, tiles_n, lower) shapes one factorisation cycles through
     int next_list = 0;
 };
 
@@ -42,6 +43,7 @@ struct Slot {
     DevBuf cov;    // P x ldC      posterior covariance / its factor
     DevBuf LinvC;  // inverted diagonal blocks of chol(cov)
     DevBuf misc;   // small scratch
+    DevBuf panelU; // panel x panel scratch of the tall-panel factorisation: L_jj^{-T} of the current diagonal block
     OzWork oz;
     int oz_planes = 7;  // digit planes of the int8 path for the work queued on this slot when ctx->ozaki == -1 (auto)
     cudaEvent_t ev[8];
@@ -59,6 +61,8 @@ struct b2gp_ctx {
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
     int trsm_strip = 256;  // widest factor solved by the one-launch strip kernel (0: recurse down to the 128 leaves)
     int oz_cluster = 2;  // 2: CTA pairs share the A digit planes by TMA multicast; 1: independent CTAs
+    int panel = 512;       // diagonal-block width of the tall-panel factorisation (potrf_tall); 0: recursive potrf_rec / trsm_rec only
+    int tall_min = 2048;   // smallest N factored by potrf_tall
     int oz_debug = 0;  // see OzArgs::debug (0 in production)
     // 0: fp64 DMMA only; 6 / 7: large rank-k updates through the int8 tcgen05 path with that many base-256 digit planes
     // (46 / 54 bits per operand); -1: 6 or 7 per factorisation from a bound on cond(K), see oz_auto_planes()

@@ -223,7 +223,8 @@ static int launch_gemm_cfg(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a) {
 
 static int gemm_tma_dispatch(b2gp_ctx* ctx, cudaStream_t st, GemmArgs& a);  // gemm_tma.cuh
 static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                          const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only);  // ozaki.cuh
+                          const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only, bool overwrite, bool transB,
+                          bool ktri);  // ozaki.cuh
 
 // C = beta*C + alpha*A*B^T.  lower_only requires a square C (m == n) whose diagonal is the matrix
 // diagonal.  `inplace_rows` marks the B <- B*Linv^T use where C aliases A: that is only safe with a
@@ -244,18 +245,23 @@ static int gemm_nt(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t
     a.alpha = alpha;
     a.beta = beta;
     a.lower_only = lower_only ? 1 : 0;
-    if (lower_only && m != n) return set_err(ctx, B2GP_ERR_ARG, "gemm_nt", "lower_only needs m == n", __FILE__, __LINE__);
+    if (lower_only && m < n) return set_err(ctx, B2GP_ERR_ARG, "gemm_nt", "lower_only needs m >= n", __FILE__, __LINE__);
     // Large rank-k updates C += alpha A B^T (the trailing updates of the factorisation and of the blocked solves) go
     // to the int8 tcgen05 path when it is enabled: measured 64 TFLOP/s-equivalent with 8 digit planes against
     // 35 for DMMA (ozaki.cuh).  It needs beta == 1, k within the int32 accumulation bound, enough 128x64 tiles to
     // fill the machine twice, and operands distinct from C (the in-place solve keeps the DMMA kernel).
     if (ctx->ozaki && beta == 1.0 && k >= 512 && C != A && C != B) {
-        const int64_t tm = ceil_div(m, 128), tn = ceil_div(n, 64);
-        const int64_t toz = lower_only ? tm * (tm + 1) : tm * tn;
+        const int64_t tm = ceil_div(m, 128), tn = ceil_div(n, 64), sq = ceil_div(n, 128);
+        const int64_t toz = lower_only ? sq * (sq + 1) + (tm - sq) * tn : tm * tn;   // lower triangle (+ the rows below it)
         if (toz >= ctx->oz_min_tiles) {
-            const int rc = ozaki_dispatch(ctx, st, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only);
+            const int rc = ozaki_dispatch(ctx, st, m, n, k, alpha, A, lda, B, ldb, C, ldc, lower_only, false, false, false);
             if (rc != B2GP_ERR_UNSUPPORTED) return rc;
         }
+    }
+    if (lower_only && m > n) {
+        // trapezoid on the fp64 kernels (their lower-only tile maps are square): the square part, then the rows below it
+        RET_IF(gemm_nt(ctx, st, n, n, k, alpha, A, lda, B, ldb, beta, C, ldc, true));
+        return gemm_nt(ctx, st, m - n, n, k, alpha, A + n * lda, lda, B, ldb, beta, C + n * ldc, ldc, false);
     }
     // Tile choice.  A 128x128 tile keeps one SM busy for 128*128*k/64 cycles (DMMA: 64 fp64 FMA/clk/SM),
     // i.e. ~17 us per k = 128, however few tiles there are; when the 128x128 grid would leave most of

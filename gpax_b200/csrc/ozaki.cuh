@@ -49,22 +49,27 @@ struct OzArgs {
     int tiles_m, tiles_n;
     int num_tiles;
     const int2* tile_list;  // [num_tiles] (ti, tj) in execution order (host-built, L2-friendly)
+    int overwrite;  // 1: C = alpha A B^T (C is not read: beta = 0; C may alias the fp64 source of A, which was copied to planes)
+    int ktri;       // 1: B is lower triangular (B[c][k] = 0 for k > c): a column tile needs only the k-blocks up to its last row
     int debug;  // 0 normal; 1 skip the global read-modify-write; 2 also skip staging barriers (timing experiments only)
     long long* prof;  // optional [gridDim.x][8]: epilogue cycles (wait acc_full, whole, C update), tiles, MMA issuer (wait TMA, wait drain, total)
 };
 
 // ---------------------------------------------------------------------------------------------- slicing
 // one CTA per row: row maximum -> exponent, then S digits per element; planes[p][row][kk]
+// trans != 0: the operand is the TRANSPOSE of the stored matrix, element (row, kk) = A[kk * lda + row] (small operands only:
+// the reads are strided)
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ A, int64_t lda, int rows, int k, int8_t* __restrict__ planes,
-                                                       int rows_pad, int kpad, double* __restrict__ scale) {
+                                                       int rows_pad, int kpad, double* __restrict__ scale, int trans) {
     __shared__ double red[8];
     const int row = blockIdx.x;
     const int tid = threadIdx.x;
+    const int64_t sr = trans ? 1 : lda, sk = trans ? lda : 1;   // strides of (row, kk)
     int e = 0;
     if (row < rows) {
         double mx = 0.0;
-        for (int kk = tid; kk < k; kk += 256) mx = fmax(mx, fabs(A[(int64_t)row * lda + kk]));
+        for (int kk = tid; kk < k; kk += 256) mx = fmax(mx, fabs(A[(int64_t)row * sr + (int64_t)kk * sk]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((tid & 31) == 0) red[tid >> 5] = mx;
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int kk = k4 + j;
-            long long I = (row < rows && kk < k) ? __double2ll_rn(A[(int64_t)row * lda + kk] * up) : 0ll;
+            long long I = (row < rows && kk < k) ? __double2ll_rn(A[(int64_t)row * sr + (int64_t)kk * sk] * up) : 0ll;
 #pragma unroll
             for (int p = S - 1; p > 0; --p) {
                 const int d = (int)(signed char)(I & 0xff);          // signed low byte
@@ -186,6 +191,14 @@ __device__ __forceinline__ void tc_wait_ld32(int (&v)[32]) {
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// k-blocks a tile of column pair / column tile `ty` runs over: all of them, or -- B lower triangular -- those up to
+// the last row of B the tile (the CTA pair's tiles, which share the A stages) touches
+__device__ __forceinline__ int oz_kb_count(const OzArgs& p, int CL, int ty) {
+    if (!p.ktri) return p.kb_count;
+    const int lim = ((CL * ty + CL) * OZ_BN + OZ_KB - 1) / OZ_KB;
+    return lim < p.kb_count ? lim : p.kb_count;
+}
+
 __device__ __forceinline__ void oz_tile_of(int x, int lower_only, int tiles_n, int& ti, int& tj) {
     if (lower_only) {  // 128 x 64 tiles of the lower triangle: row block ti owns column tiles 0 .. 2 ti + 1
         int t = (int)((sqrt(4.0 * (double)x + 1.0) - 1.0) * 0.5);
@@ -245,7 +258,8 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
                 const int2 tt = p.tile_list[tile];
                 const int row0 = tt.x * OZ_BM, col0 = (CL * tt.y + (int)crank) * OZ_BN;
-                for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+                const int kbn = oz_kb_count(p, CL, tt.y);
+                for (int kb = 0; kb < kbn; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
                     mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);   // bytes landing in THIS CTA's stage, whoever fetches them
@@ -272,7 +286,8 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 mbar_wait(acc_empty, (tcount & 1u) ^ 1u);   // epilogue of the previous tile has drained TMEM
                 m_empty += clock64() - e0;
                 tc_fence_after();
-                for (int kb = 0; kb < p.kb_count; ++kb, ++it) {
+                const int kbn = oz_kb_count(p, CL, p.tile_list[tile].y);
+                for (int kb = 0; kb < kbn; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     const long long f0 = p.prof ? clock64() : 0;
                     mbar_wait(full0 + 8 * s, ph);
@@ -329,7 +344,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             const long long t1 = clock64();
             c_wait += t1 - t0;
             // pull the tile of C towards L2 now: the drain below takes longer than an HBM round trip
-            if (p.debug == 0 && (cc == 0 || cc == 15)) {
+            if (p.debug == 0 && !p.overwrite && (cc == 0 || cc == 15)) {
 #pragma unroll
                 for (int c16 = 0; c16 < 4; ++c16) {
                     const int gc = col0 + 16 * c16 + cc;
@@ -384,7 +399,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
 #pragma unroll
                     for (int it = 0; it < 16; ++it) {
                         const int gr = ti * OZ_BM + it * 8 + (et >> 4);
-                        oldv[it] = (gr < p.m && gc < p.n && !(p.lower_only && gc > gr)) ? p.C[(int64_t)gr * p.ldc + gc] : 0.0;
+                        oldv[it] = (!p.overwrite && gr < p.m && gc < p.n && !(p.lower_only && gc > gr)) ? p.C[(int64_t)gr * p.ldc + gc] : 0.0;
                     }
 #pragma unroll
                     for (int it = 0; it < 16; ++it) {
@@ -427,24 +442,32 @@ static bool make_tmap_u8(CUtensorMap* map, const int8_t* base, int64_t rows_tota
 }
 
 // C[m,n] += alpha * A[m,k] B[n,k]^T  (lower_only: j <= i, A == B allowed) through the int8 tensor cores
+// Modes (OzMode): overwrite -- C = alpha A B^T, C not read (it may alias A's fp64 storage: the operands are copied to digit
+// planes first); transB -- B is given transposed (element (j, kk) at B[kk * ldb + j]); ktri -- B is lower triangular.
+// lower_only with m > n is the "trapezoid" of a factorisation with right-hand-side rows riding below the matrix: rows
+// < n update j <= i only, the rows below update all n columns.
+struct OzMode {
+    bool overwrite = false, transB = false, ktri = false;
+};
 template <int S>
 static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                         int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
+                         int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only, OzMode mode = OzMode()) {
     if (m <= 0 || n <= 0 || k <= 0) return B2GP_OK;
     if (k > OZ_K_MAX) return B2GP_ERR_UNSUPPORTED;  // int32 accumulation bound (the dispatcher splits longer k)
     const int64_t kpad = round_up(k, OZ_KB);
     const int64_t ra = round_up(m, 128), rb = round_up(n, 128);
-    const bool same = (A == B && lda == ldb && m == n);
+    const bool same = (A == B && lda == ldb && n <= m && !mode.transB);   // B's rows are the first n rows of A: one set of planes
     RET_IF(ensure(ctx, w.planesA, (size_t)S * ra * kpad));
     RET_IF(ensure(ctx, w.scaleA, (size_t)ra * 8));
-    oz_slice_kernel<S><<<(unsigned)ra, 256, 0, st>>>(A, lda, (int)m, (int)k, (int8_t*)w.planesA.p, (int)ra, (int)kpad, (double*)w.scaleA.p);
+    oz_slice_kernel<S><<<(unsigned)ra, 256, 0, st>>>(A, lda, (int)m, (int)k, (int8_t*)w.planesA.p, (int)ra, (int)kpad, (double*)w.scaleA.p, 0);
     const int8_t* pb = (const int8_t*)w.planesA.p;
     const double* sb = (const double*)w.scaleA.p;
     int64_t rbp = ra;
     if (!same) {
         RET_IF(ensure(ctx, w.planesB, (size_t)S * rb * kpad));
         RET_IF(ensure(ctx, w.scaleB, (size_t)rb * 8));
-        oz_slice_kernel<S><<<(unsigned)rb, 256, 0, st>>>(B, ldb, (int)n, (int)k, (int8_t*)w.planesB.p, (int)rb, (int)kpad, (double*)w.scaleB.p);
+        oz_slice_kernel<S><<<(unsigned)rb, 256, 0, st>>>(B, ldb, (int)n, (int)k, (int8_t*)w.planesB.p, (int)rb, (int)kpad, (double*)w.scaleB.p,
+                                                         mode.transB ? 1 : 0);
         pb = (const int8_t*)w.planesB.p;
         sb = (const double*)w.scaleB.p;
         rbp = rb;
@@ -466,6 +489,8 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     a.ldc = ldc;
     a.alpha = alpha;
     a.lower_only = lower_only ? 1 : 0;
+    a.overwrite = mode.overwrite ? 1 : 0;
+    a.ktri = mode.ktri ? 1 : 0;
     a.tiles_m = (int)ceil_div(m, OZ_BM);
     a.tiles_n = (int)ceil_div(n, OZ_BN);
     // Tile order.  One round of the persistent loop runs sm_count consecutive list entries concurrently and, tiles
@@ -478,8 +503,9 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     for (auto& l : w.lists)
         if (l.tm == a.tiles_m && l.tn == a.tiles_n && l.lower == a.lower_only && l.cl == CL) tl = &l;
     if (!tl) {
+        // one factorisation cycles through ~2 N / panel distinct shapes; they repeat from draw to draw
         tl = &w.lists[w.next_list];
-        w.next_list = (w.next_list + 1) % 8;
+        w.next_list = (w.next_list + 1) % OZ_LISTS;
         tl->host.clear();
         const int G = 8;
         for (int b0 = 0; b0 < a.tiles_m; b0 += G) {
@@ -539,17 +565,22 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
 }
 
 static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
-                          const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only) {
+                          const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only, bool overwrite, bool transB, bool ktri) {
     Slot* sl = slot_of(ctx, st);
     OzWork* w = sl ? &sl->oz : &ctx->slots[0].oz;
     const int planes = oz_planes_for(ctx, st);
     for (int64_t k0 = 0; k0 < k; k0 += OZ_K_MAX) {
         const int64_t kc = k - k0 < OZ_K_MAX ? k - k0 : OZ_K_MAX;
+        OzMode mode;
+        mode.overwrite = overwrite && k0 == 0;      // later k-chunks accumulate onto the first
+        mode.transB = transB;
+        mode.ktri = ktri && k <= OZ_K_MAX;
+        const double* Bk = transB ? B + k0 * ldb : B + k0;
         int rc;
         if (planes == 6)
-            rc = ozaki_gemm_nt<6>(ctx, st, *w, m, n, kc, alpha, A + k0, lda, B + k0, ldb, C, ldc, lower_only);
+            rc = ozaki_gemm_nt<6>(ctx, st, *w, m, n, kc, alpha, A + k0, lda, Bk, ldb, C, ldc, lower_only, mode);
         else
-            rc = ozaki_gemm_nt<7>(ctx, st, *w, m, n, kc, alpha, A + k0, lda, B + k0, ldb, C, ldc, lower_only);
+            rc = ozaki_gemm_nt<7>(ctx, st, *w, m, n, kc, alpha, A + k0, lda, Bk, ldb, C, ldc, lower_only, mode);
         if (rc != B2GP_OK) return rc;
     }
     return B2GP_OK;

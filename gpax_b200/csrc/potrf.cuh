@@ -576,4 +576,59 @@ static int potrf_rec(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int
     return potrf_rec(ctx, st, A22, lda, n2, Linv + (n1 / B2GP_LEAF) * 128 * 128, info, index_base + n1);
 }
 
+// ---------------------------------------------------------------------------------------------- tall-panel factorisation
+// potrf_tall(A, n, r): factor the n x n diagonal block at A and solve the r rows stored below it,
+//     A[n .. n+r, 0 .. n)  <-  A[n .. n+r, 0 .. n) L^{-T},
+// where "the rows below" are the rest of the matrix AND any right-hand-side rows appended to it (the posterior stores
+// [k_pX; y^T] under k_XX, so the solve V^T = k_pX L^{-T} of gp.py:272-273 rides along with the factorisation's own panel
+// solves instead of being a second pass over L).  Recursion:
+//     n <= panel:  potrf_rec on the block (128-wide leaves, fp64), U = L^{-T} by solving the identity, then ONE int8
+//                  tcgen05 GEMM  rows <- rows U  (k = panel, B operand read transposed and k-triangular, C overwrites A's
+//                  storage) for all r rows at once;
+//     else:        potrf_tall(A11, n1, n2 + r);   [A22; E2] -= [A21; E1] A21^T  (one int8 GEMM over the lower
+//                  trapezoid, k = n1);   potrf_tall(A22, n2, r).
+// Against potrf_rec / trsm_rec this replaces the trsm recursion (2 N / 128 strip and thin-GEMM launches at 5-13 % of the
+// DMMA peak) by N / panel machine-filling int8 GEMMs at the cost of 2x the flops of the diagonal-block solves
+// (N^2 panel flops, 1.4e11 at N = 16384 against 1.5e12 for the factorisation), and every GEMM is as tall as the matrix.
+static inline bool use_tall(const b2gp_ctx* ctx, int64_t n) { return ctx->ozaki != 0 && ctx->panel >= 128 && n >= ctx->tall_min; }
+
+static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* rows, int64_t ldr, int64_t r, const double* L,
+                                int64_t ldl, int64_t n, const double* Linv128) {
+    const int64_t ldu = round_up(n, 8);
+    RET_IF(ensure(ctx, sl.panelU, (size_t)n * ldu * 8));
+    double* U = (double*)sl.panelU.p;
+    set_identity_kernel<<<grid_for(n * n), 256, 0, st>>>(U, ldu, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    RET_IF(trsm_rec(ctx, st, U, ldu, n, L, ldl, n, Linv128));          // U = I L^{-T}
+    // rows <- rows L^{-T} = rows (L^{-1})^T: NT GEMM whose B operand L^{-1} is U read transposed
+    return ozaki_dispatch(ctx, st, r, n, n, 1.0, rows, ldr, U, ldu, rows, ldr, false, true, true, true);
+}
+
+static int potrf_tall(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* A, int64_t lda, int64_t n, int64_t r, double* Linv128,
+                      int* info, int64_t index_base) {
+    if (n <= 0) return B2GP_OK;
+    const int64_t NB = ctx->panel;
+    if (n <= NB) {
+        RET_IF(potrf_rec(ctx, st, A, lda, n, Linv128, info, index_base));
+        if (r > 0) RET_IF(panel_solve_all_rows(ctx, st, sl, A + n * lda, lda, r, A, lda, n, Linv128));
+        return B2GP_OK;
+    }
+    const int64_t nblk = ceil_div(n, NB);
+    const int64_t n1 = (nblk + 1) / 2 * NB, n2 = n - n1;
+    RET_IF(potrf_tall(ctx, st, sl, A, lda, n1, n2 + r, Linv128, info, index_base));
+    double* Pn = A + n1 * lda;   // [A21; E1]: n2 + r rows, n1 columns, solved
+    RET_IF(gemm_nt(ctx, st, n2 + r, n2, n1, -1.0, Pn, lda, Pn, lda, 1.0, Pn + n1, lda, true));
+    return potrf_tall(ctx, st, sl, Pn + n1, lda, n2, r, Linv128 + (n1 / B2GP_LEAF) * 128 * 128, info, index_base + n1);
+}
+
+// factorisation (+ solve of r appended rows) by whichever scheme fits the size
+static int potrf_auto(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int64_t n, int64_t r, double* Linv128, int* info) {
+    Slot* sl = slot_of(ctx, st);
+    if (sl && use_tall(ctx, n)) return potrf_tall(ctx, st, *sl, A, lda, n, r, Linv128, info, 0);
+    RET_IF(potrf_rec(ctx, st, A, lda, n, Linv128, info, 0));
+    if (r > 0) RET_IF(trsm_rec(ctx, st, A + n * lda, lda, r, A, lda, n, Linv128));
+    return B2GP_OK;
+}
+
 static inline int64_t linv_bytes(int64_t n) { return ceil_div(n, B2GP_LEAF) * 128 * 128 * (int64_t)sizeof(double); }

@@ -300,3 +300,35 @@ def test_kernel_functions_shapes(gp):
             for ell in (np.array(1.0), np.ones(d)):
                 K = fn(X, X, {"k_length": ell, "k_scale": np.array(1.0), "period": np.array(1.0)})
                 assert isinstance(K, np.ndarray) and K.shape == (5, 5)
+
+
+# ------------------------------------------------------------------ tall-panel factorisation (N >= 2048, int8 path on)
+@pytest.mark.parametrize("kname,N,P", [("RBF", 2500, 300), ("Matern", 3100, 129), ("Periodic", 2048, 64)])
+def test_tall_panel_path_vs_oracle(gp, kname, N, P):
+    """N >= 2048 takes potrf_tall (potrf.cuh): the right-hand-side rows [k_pX; y] ride under k_XX through int8 panel GEMMs
+    with explicit inverses of the 512-wide diagonal blocks.  Ragged N (not a multiple of 512 / 128), all three kernels,
+    mean + full covariance against the oracle, and against the recursive scheme (panel = 0)."""
+    rng = np.random.default_rng(N + P)
+    d = 2
+    X = rng.uniform(0, 1, (N, d))
+    y = np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1]) + 0.1 * rng.standard_normal(N)
+    Xn = rng.uniform(0, 1, (P, d))
+    params = {"k_length": np.array([0.25, 0.35]), "k_scale": 1.1, "noise": 0.05, "period": 0.9}
+    rmean, rcov = oracle.exact_posterior_chol(X, y, Xn, params, kname)
+    K = oracle.get_kernel(kname)(X, X, params, params["noise"])
+    cond = np.linalg.cond(K)
+    tol = RTOL * max(1.0, cond / 1e5)
+    m = gp.ExactGP(d, kname)
+    m.X_train, m.y_train = X, y
+    outs = {}
+    for panel in (512, 256, 0):
+        m.ctx.set_option("panel", panel)
+        mean, cov = m.get_mvn_posterior(Xn, params)
+        assert_close(mean, rmean, tol, f"mean panel={panel} cond={cond:.1e}")
+        assert_close(cov, rcov, tol, f"cov panel={panel} cond={cond:.1e}")
+        outs[panel] = mean
+    m.ctx.set_option("panel", 512)
+    # a failed factorisation still gives NaNs, not an exception, on this path
+    bad = dict(params, k_scale=-1.0)
+    mean, cov = m.get_mvn_posterior(Xn, bad)
+    assert np.isnan(mean).all() and np.isnan(cov).all()
