@@ -9,8 +9,10 @@ from .kernels import MaternKernel, PeriodicKernel, RBFKernel, get_kernel
 from .gp import ExactGP
 from .vigp import viGP
 from .sparse_gp import viSparseGP
+from .variants import MeasuredNoiseGP, UIGP, VarNoiseGP, vExactGP
+from . import acquisition
 from ._ffi import B200GPError, Context, default_context
 
 __version__ = "0.1.0"
-__all__ = ["ExactGP", "viGP", "viSparseGP", "RBFKernel", "MaternKernel", "PeriodicKernel", "get_kernel",
+__all__ = ["ExactGP", "viGP", "viSparseGP", "MeasuredNoiseGP", "VarNoiseGP", "vExactGP", "UIGP", "acquisition", "RBFKernel", "MaternKernel", "PeriodicKernel", "get_kernel",
            "kernels", "utils", "Context", "default_context", "B200GPError"]

@@ -64,6 +64,10 @@ SIGNATURES = {
     "b2gp_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int, C.c_int64,
                                  _vp, C.c_int, C.c_double, C.c_uint, _vp, _vp, _vp, _vp, C.c_int64, _vp, _vp,
                                  C.POINTER(Timing)]),
+    "b2gp_posterior_batch": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int,
+                                       C.c_int64, _vp, _vp, C.c_int64, C.c_int, C.c_double, C.c_uint, _vp, _vp, _vp, _vp,
+                                       C.c_int64, _vp, _vp, C.POINTER(Timing)]),
+    "b2gp_mll_v": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, _vp, C.c_double, C.c_uint, _dp, _vp, _vp, _vp, _ip]),
     "b2gp_sparse_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int,
                                         _vp, C.c_int, C.c_double, C.c_uint, _vp, _vp, _vp, _vp, C.POINTER(Timing)]),
     "b2gp_mll": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, C.c_uint, _dp, _vp, _vp, _ip]),
@@ -76,6 +80,12 @@ SIGNATURES = {
     "b2gp_potrf_inv": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, _ip]),
     "b2gp_trsm_inv": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64]),
     "b2gp_rowdot": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_double, _vp, _vp, C.c_int]),
+    "b2gp_mvn_sample": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_uint]),
+    "b2gp_acq_moments": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, _vp,
+                                   C.c_uint]),
+    "b2gp_acq_samples": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, _vp, _vp,
+                                   _vp, C.c_uint]),
+    "b2gp_kg": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int64, C.c_double, C.c_double, C.c_int, _vp, C.c_uint]),
     "b2gp_copy2d": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int64, C.c_int64]),
 }
 
@@ -249,15 +259,23 @@ class Context:
 
     # ---- the posterior (host arrays in / out)
     def posterior(self, kind, Xtr, yres, Xnew, theta, noiseless=False, jitter=1e-6, want=("mean", "cov"),
-                  eps=None, timing=False):
-        """theta: [S, d+3] rows (lengthscale[d], k_scale, noise, period); yres [N] or [S, N]."""
+                  eps=None, timing=False, noise_vec=None):
+        """theta: [S, d+3] rows (lengthscale[d], k_scale, noise, period); yres [N] or [S, N].  Xtr [N, d] or per member
+        [S, N, d]; Xnew [P, d] or [S, P, d]; noise_vec None, [N] or [S, N] (per-point noise variances on k_XX's diagonal)."""
         Xtr, Xnew = _f64(Xtr), _f64(Xnew)
-        N, d = Xtr.shape
-        P = Xnew.shape[0]
+        N, d = Xtr.shape[-2:]
+        P = Xnew.shape[-2]
         theta = _f64(theta).reshape(-1, d + 3)
         S = theta.shape[0]
         yres = _f64(yres)
         stride = 0 if yres.ndim == 1 else yres.shape[1]
+        xs = 0 if Xtr.ndim == 2 else N * d
+        xns = 0 if Xnew.ndim == 2 else P * d
+        nv = None if noise_vec is None else _f64(noise_vec)
+        nvs = 0 if nv is None or nv.ndim == 1 else N
+        for a, n_ in ((Xtr, xs), (Xnew, xns), (nv, nvs)):
+            if a is not None and n_ and a.shape[0] != S:
+                raise ValueError("per-member arrays need a leading axis of length S = theta.shape[0]")
         flags = 0
         mean = var = cov = samp = None
         if "mean" in want:
@@ -277,17 +295,18 @@ class Context:
             samp = np.empty((S, n_samp, P))
         info = np.zeros(S, dtype=np.int32)
         t = Timing()
-        self._check(self.lib.b2gp_posterior(
-            self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(Xtr), N, _ptr(yres), stride, _ptr(Xnew), P, d, S,
-            _ptr(theta), int(bool(noiseless)), float(jitter), flags, _ptr(mean), _ptr(var), _ptr(cov), _ptr(eps), n_samp,
-            _ptr(samp), info.ctypes.data_as(_vp), C.byref(t) if timing else None))
+        self._check(self.lib.b2gp_posterior_batch(
+            self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(Xtr), xs, N, _ptr(yres), stride, _ptr(Xnew), xns, P, d, S,
+            _ptr(theta), _ptr(nv), nvs, int(bool(noiseless)), float(jitter), flags, _ptr(mean), _ptr(var), _ptr(cov), _ptr(eps),
+            n_samp, _ptr(samp), info.ctypes.data_as(_vp), C.byref(t) if timing else None))
         out = {"mean": mean, "var": var, "cov": cov, "y_sampled": samp, "info": info}
         if timing:
             out["timing"] = t.as_dict()
         return out
 
-    def mll(self, kind, X, yres, theta, jitter=1e-6, want_grad=True, want_alpha=False):
-        """log marginal likelihood, its gradient w.r.t. log(lengthscale[d], k_scale, noise, period), alpha = K^-1 y"""
+    def mll(self, kind, X, yres, theta, jitter=1e-6, want_grad=True, want_alpha=False, noise_vec=None):
+        """log marginal likelihood, its gradient w.r.t. log(lengthscale[d], k_scale, noise, period), alpha = K^-1 y.
+        With noise_vec [N] (per-point noise variances on the diagonal) the return gains d value / d noise_vec."""
         X, yres = _f64(X), _f64(yres)
         N, d = X.shape
         theta = _f64(theta).reshape(d + 3)
@@ -295,9 +314,16 @@ class Context:
         grad = np.zeros(d + 3) if want_grad else None
         alpha = np.zeros(N) if want_alpha else None
         info = C.c_int(0)
-        self._check(self.lib.b2gp_mll(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), N, _ptr(yres), d,
-                                      _ptr(theta), float(jitter), 0, C.byref(val), _ptr(grad), _ptr(alpha), C.byref(info)))
-        return val.value, grad, alpha, info.value
+        if noise_vec is None:
+            self._check(self.lib.b2gp_mll(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), N, _ptr(yres), d,
+                                          _ptr(theta), float(jitter), 0, C.byref(val), _ptr(grad), _ptr(alpha), C.byref(info)))
+            return val.value, grad, alpha, info.value
+        nv = _f64(noise_vec).reshape(N)
+        gnv = np.zeros(N) if want_grad else None
+        self._check(self.lib.b2gp_mll_v(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), N, _ptr(yres), d,
+                                        _ptr(theta), _ptr(nv), float(jitter), 0, C.byref(val), _ptr(grad), _ptr(alpha), _ptr(gnv),
+                                        C.byref(info)))
+        return val.value, grad, alpha, info.value, gnv
 
     def sparse_elbo(self, kind, Xu, X, yres, theta, jitter=1e-6):
         """VFE bound of the sparse GP, its gradient w.r.t. log(lengthscale[d], k_scale, noise, period) and w.r.t. Xu"""
@@ -337,6 +363,59 @@ class Context:
             info.ctypes.data_as(_vp), C.byref(t)))
         return {"mean": mean, "var": var, "cov": cov, "info": int(info[0]), "timing": t.as_dict()}
 
+
+ACQ = {"EI": 0, "UCB": 1, "UE": 2, "POI": 3}
+
+
+def _acq_moments(self, kind, mean, var, best_f=None, param=0.0, maximize=False):
+    """acquisition function `kind` on moments [P] or [R, P] (host arrays)"""
+    var = _f64(var)
+    shape = var.shape
+    var = var.reshape(-1, shape[-1])
+    mean = None if mean is None else _f64(mean).reshape(var.shape)
+    out = np.empty_like(var)
+    self._check(self.lib.b2gp_acq_moments(self.h, ACQ[kind], _ptr(mean), _ptr(var), var.shape[0], var.shape[1],
+                                          int(best_f is not None), float(best_f or 0.0), float(param), int(bool(maximize)),
+                                          _ptr(out), 0))
+    return out.reshape(shape)
+
+
+def _acq_samples(self, kind, y, best_f=None, param=0.0, maximize=False):
+    """moments over the rows of y [R, P], then the acquisition function; returns (acq, mean, var)"""
+    y = _f64(y)
+    y = y.reshape(-1, y.shape[-1])
+    R, P = y.shape
+    out, mean, var = np.empty(P), np.empty(P), np.empty(P)
+    self._check(self.lib.b2gp_acq_samples(self.h, ACQ[kind], _ptr(y), R, P, int(best_f is not None), float(best_f or 0.0),
+                                          float(param), int(bool(maximize)), _ptr(out), _ptr(mean), _ptr(var), 0))
+    return out, mean, var
+
+
+def _kg(self, mean, cov, ysim, diag_sub, noise_plus_jitter, maximize=True):
+    mean, cov, ysim = _f64(mean), _f64(cov), _f64(ysim)
+    P = mean.shape[0]
+    ysim = ysim.reshape(-1, P)
+    out = np.empty(P)
+    self._check(self.lib.b2gp_kg(self.h, _ptr(mean), _ptr(cov), P, _ptr(ysim), ysim.shape[0], float(diag_sub),
+                                 float(noise_plus_jitter), int(bool(maximize)), _ptr(out), 0))
+    return out
+
+
+def _mvn_sample(self, mean, cov, eps):
+    """mean [S, P], cov [S, P, P], eps [S, n, P] -> (mean + chol(cov) eps [S, n, P], info [S])"""
+    mean, cov, eps = _f64(mean), _f64(cov), _f64(eps)
+    P = mean.shape[-1]
+    mean, cov = mean.reshape(-1, P), cov.reshape(-1, P, P)
+    S = mean.shape[0]
+    eps = eps.reshape(S, -1, P)
+    y = np.empty_like(eps)
+    info = np.zeros(S, dtype=np.int32)
+    self._check(self.lib.b2gp_mvn_sample(self.h, _ptr(mean), _ptr(cov), S, P, _ptr(eps), eps.shape[1], _ptr(y),
+                                         info.ctypes.data_as(_vp), 0))
+    return y, info
+
+
+Context.acq_moments, Context.acq_samples, Context.kg, Context.mvn_sample = _acq_moments, _acq_samples, _kg, _mvn_sample
 
 _default_ctx = None
 

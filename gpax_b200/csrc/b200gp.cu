@@ -14,6 +14,7 @@
 #include "posterior.cuh"
 #include "potrf.cuh"
 #include "sparse_elbo.cuh"
+#include "acq.cuh"
 
 // ------------------------------------------------------------------------------------------ helpers
 namespace {
@@ -518,12 +519,25 @@ struct StageEvents {
 };
 }
 
-extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t N, const double* yres, int64_t yres_stride,
-                              const double* Xnew, int64_t P, int d, int64_t S, const double* theta, int noiseless, double jitter,
-                              unsigned flags, double* mean, double* var, double* cov, const double* eps, int64_t n_samp,
-                              double* y_sampled, int* info, b2gp_timing* timing) {
+// diag(A) += v   (per-point noise variances: mngp.py:96, hskgp.py:147)
+__global__ void add_diag_vec_kernel(double* A, int64_t ld, int64_t n, const double* __restrict__ v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) A[i * ld + i] += v[i];
+}
+
+// The posterior with everything that may vary per draw: the training inputs (xtr_stride doubles between draws; 0 =
+// shared), the test inputs (xnew_stride), the targets (yres_stride) and an optional vector of per-point noise variances
+// added to the diagonal of k_XX (nv_stride between draws; 0 = shared).  b2gp_posterior is the all-shared special case.
+static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xtr_stride, int64_t N, const double* yres,
+                          int64_t yres_stride, const double* Xnew, int64_t xnew_stride, int64_t P, int d, int64_t S,
+                          const double* theta, const double* noise_vec, int64_t nv_stride, int noiseless, double jitter,
+                          unsigned flags, double* mean, double* var, double* cov, const double* eps, int64_t n_samp,
+                          double* y_sampled, int* info, b2gp_timing* timing) {
     if (!ctx) return B2GP_ERR_ARG;
     ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, xtr_stride == 0 || xtr_stride >= N * d);
+    ARG_CHECK(ctx, xnew_stride == 0 || xnew_stride >= P * d);
+    ARG_CHECK(ctx, nv_stride == 0 || nv_stride >= N);
     ARG_CHECK(ctx, Xtr && yres && Xnew && theta && info);
     ARG_CHECK(ctx, N >= 1 && P >= 1 && S >= 1 && d >= 1 && d <= GRAM_MAX_D);
     ARG_CHECK(ctx, yres_stride == 0 || yres_stride >= N);
@@ -544,11 +558,12 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
 
     // ---- inputs
     const int nth = d + 3;
-    const double *dXtr, *dy, *dXnew, *dtheta, *deps = nullptr;
+    const double *dXtr, *dy, *dXnew, *dtheta, *deps = nullptr, *dnv = nullptr;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st0));
-    RET_IF(stage_in(ctx, st0, ctx->d_in[0], Xtr, (size_t)N * d * 8, dev, &dXtr));
+    RET_IF(stage_in(ctx, st0, ctx->d_in[0], Xtr, (size_t)(xtr_stride ? S * xtr_stride : N * d) * 8, dev, &dXtr));
     RET_IF(stage_in(ctx, st0, ctx->d_in[1], yres, (size_t)(yres_stride ? S * yres_stride : N) * 8, dev, &dy));
-    RET_IF(stage_in(ctx, st0, ctx->d_in[2], Xnew, (size_t)P * d * 8, dev, &dXnew));
+    RET_IF(stage_in(ctx, st0, ctx->d_in[2], Xnew, (size_t)(xnew_stride ? S * xnew_stride : P * d) * 8, dev, &dXnew));
+    if (noise_vec) RET_IF(stage_in(ctx, st0, ctx->d_in[6], noise_vec, (size_t)(nv_stride ? S * nv_stride : N) * 8, dev, &dnv));
     RET_IF(stage_in(ctx, st0, ctx->d_in[3], theta, (size_t)S * nth * 8, dev, &dtheta));
     if (want_samp) RET_IF(stage_in(ctx, st0, ctx->d_in[4], eps, (size_t)S * n_samp * P * 8, dev, &deps));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st0));
@@ -617,7 +632,7 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     // leaves it so, and it is re-validated -- together with the factor's `info` -- only after the call's work has
     // completed on the device (end of this function).
     bool reuse = false;
-    const bool cacheable = (S == 1 && !dev);
+    const bool cacheable = (S == 1 && !dev && !noise_vec);
     if (cacheable) {
         auto& fc = ex->fcache;
         reuse = fc.valid && fc.kind == kind && fc.N == N && fc.d == d && fc.jitter == jitter &&
@@ -634,6 +649,8 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
         double* Vt = A + N * ldA;
         double* Linv = (double*)sl.Linv.p;
         const double* th = dtheta + s * nth;
+        const double* dXtr_s = dXtr + s * xtr_stride;
+        const double* dXnew_s = dXnew + s * xnew_stride;
         const bool fused_solve = !reuse && use_tall(ctx, N);   // the P-side solve rides along with the factorisation
         int* inf = dinfo + s;
         int* inf2 = dinfo + S + s;
@@ -642,16 +659,21 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
             CUDA_TRY(ctx, cudaEventRecord(sev[s].e[0], st));
         }
         // factorisation and P-side solve: 6 or 7 digit planes from the trace bound on cond(K); covariance / sampling: 7
-        sl.oz_planes = htheta.empty() ? 7 : oz_auto_planes((double)N, htheta[s * nth + d], htheta[s * nth + d + 1], jitter);
+        sl.oz_planes = (htheta.empty() || noise_vec) ? 7 : oz_auto_planes((double)N, htheta[s * nth + d], htheta[s * nth + d + 1], jitter);
         auto rhs_rows = [&]() -> int {
             // k_pX = kernel(X_new, X_train, params, jitter=0.0)  (gp.py:268); same-shape inputs add 0 there
-            RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXtr, N, d, th, 0.0, 0.0, 0, 0, Vt, ldV));
+            RET_IF(launch_gram(ctx, st, kind, dXnew_s, P, dXtr_s, N, d, th, 0.0, 0.0, 0, 0, Vt, ldV));
             CUDA_TRY(ctx, cudaMemcpyAsync(Vt + P * ldV, dy + (yres_stride ? s * yres_stride : 0), (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
             return B2GP_OK;
         };
         if (!reuse) {
             // k_XX = kernel(X_train, X_train, params, noise, jitter)  (gp.py:269) -- lower triangle only
-            RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXtr, N, d, th, 1.0, jitter, 1, 1, A, ldA));
+            RET_IF(launch_gram(ctx, st, kind, dXtr_s, N, dXtr_s, N, d, th, 1.0, jitter, 1, 1, A, ldA));
+            if (dnv) {
+                add_diag_vec_kernel<<<grid_for(N), 256, 0, st>>>(A, ldA, N, dnv + s * nv_stride);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches++;
+            }
             if (fused_solve) RET_IF(rhs_rows());
             if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
             // factor instead of jnp.linalg.inv (gp.py:271); with the tall-panel scheme also [V^T; w^T] = [k_pX; y^T] L^{-T}
@@ -682,7 +704,7 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
             // cov = k_pp - V^T V  (gp.py:267, 272), lower tiles then mirrored -> exactly symmetric
             double* C = want_cov ? dcov + s * P * P : (double*)sl.cov.p;
             const int64_t ldc = want_cov ? P : ldC;
-            RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXnew, P, d, th, noise_mult_new, jitter, 1, 1, C, ldc));
+            RET_IF(launch_gram(ctx, st, kind, dXnew_s, P, dXnew_s, P, d, th, noise_mult_new, jitter, 1, 1, C, ldc));
             RET_IF(gemm_nt(ctx, st, P, P, N, -1.0, Vt, ldV, Vt, ldV, 1.0, C, ldc, true));
             dim3 g2((unsigned)ceil_div(P, 32), (unsigned)ceil_div(P, 32)), b2(32, 32);
             mirror_lower_kernel<<<g2, b2, 0, st>>>(C, ldc, P);
@@ -795,6 +817,23 @@ extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_
     t.gram_bytes = (double)S * (8.0 * n * n / 2.0 + 8.0 * n * p + (need_cov ? 8.0 * p * p : 0.0));
     if (timing) *timing = t;
     return B2GP_OK;
+}
+
+extern "C" int b2gp_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t N, const double* yres, int64_t yres_stride,
+                              const double* Xnew, int64_t P, int d, int64_t S, const double* theta, int noiseless, double jitter,
+                              unsigned flags, double* mean, double* var, double* cov, const double* eps, int64_t n_samp,
+                              double* y_sampled, int* info, b2gp_timing* timing) {
+    return posterior_impl(ctx, kind, Xtr, 0, N, yres, yres_stride, Xnew, 0, P, d, S, theta, nullptr, 0, noiseless, jitter, flags, mean,
+                          var, cov, eps, n_samp, y_sampled, info, timing);
+}
+
+extern "C" int b2gp_posterior_batch(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xtr_stride, int64_t N, const double* yres,
+                                    int64_t yres_stride, const double* Xnew, int64_t xnew_stride, int64_t P, int d, int64_t S,
+                                    const double* theta, const double* noise_vec, int64_t noise_vec_stride, int noiseless,
+                                    double jitter, unsigned flags, double* mean, double* var, double* cov, const double* eps,
+                                    int64_t n_samp, double* y_sampled, int* info, b2gp_timing* timing) {
+    return posterior_impl(ctx, kind, Xtr, xtr_stride, N, yres, yres_stride, Xnew, xnew_stride, P, d, S, theta, noise_vec,
+                          noise_vec_stride, noiseless, jitter, flags, mean, var, cov, eps, n_samp, y_sampled, info, timing);
 }
 
 // ------------------------------------------------------------------------------------------ sparse posterior
@@ -1157,9 +1196,18 @@ extern "C" int b2gp_copy2d(b2gp_ctx* ctx, double* dst, int64_t ldd, const double
 // value and gradient (w.r.t. log lengthscale[d], log k_scale, log noise, log period) of the exact-GP log marginal
 // likelihood -- see mll.cuh.  X[N,d], yres[N] host or device pointers (flags); theta is a HOST pointer (d+3);
 // value, grad[d+3] and the optional alpha[N] = K^{-1} yres are HOST outputs.
-extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d, const double* theta,
-                        double jitter, unsigned flags, double* value, double* grad, double* alpha_out, int* info) {
+// g[i] = 1/2 (alpha_i^2 - Kinv_ii): d log N(y; 0, K) / d K_ii, the gradient w.r.t. a per-point noise variance
+__global__ void mll_diag_grad_kernel(const double* __restrict__ alpha, const double* __restrict__ Kinv, int64_t ldk, int64_t n,
+                                     double* __restrict__ g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) g[i] = 0.5 * (alpha[i] * alpha[i] - Kinv[i * ldk + i]);
+}
+
+static int mll_impl(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d, const double* theta,
+                    const double* noise_vec, double jitter, unsigned flags, double* value, double* grad, double* alpha_out,
+                    double* grad_noise_vec, int* info) {
     if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, !grad_noise_vec || grad);
     ARG_CHECK(ctx, kind >= 0 && kind <= 2);
     ARG_CHECK(ctx, X && yres && theta && value && info);
     ARG_CHECK(ctx, N >= 1 && d >= 1 && d <= MLL_MAX_D);
@@ -1172,10 +1220,11 @@ extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, con
     CallTimer tm(ctx);
     RET_IF(tm.begin(st));
     const int nth = d + 3;
-    const double *dX, *dy, *dth;
+    const double *dX, *dy, *dth, *dnv = nullptr;
     RET_IF(stage_in(ctx, st, ctx->d_in[0], X, (size_t)N * d * 8, dev, &dX));
     RET_IF(stage_in(ctx, st, ctx->d_in[1], yres, (size_t)N * 8, dev, &dy));
     RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, false, &dth));
+    if (noise_vec) RET_IF(stage_in(ctx, st, ctx->d_in[6], noise_vec, (size_t)N * 8, dev, &dnv));
     const int64_t ld = round_up(N, 8);
     const int64_t tiles = ceil_div(N, MLL_TILE);
     RET_IF(ensure(ctx, sl.A, (size_t)N * ld * 8));
@@ -1191,6 +1240,11 @@ extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, con
     double* sc = alpha + ld;             // [0] sum log L_ii, [1] |w|^2, [8..8+nth) grad
     double* partial = sc + 64;
     RET_IF(launch_gram(ctx, st, kind, dX, N, dX, N, d, dth, 1.0, jitter, 1, 1, A, ld));
+    if (dnv) {   // k + diag(measured_noise) / k + diag(exp(log_var)): mngp.py:96, hskgp.py:147
+        add_diag_vec_kernel<<<grid_for(N), 256, 0, st>>>(A, ld, N, dnv);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
     RET_IF(potrf_rec(ctx, st, A, ld, N, Linv, dinfo, 0));
     CUDA_TRY(ctx, cudaMemcpyAsync(w, dy, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
     RET_IF(trsm_rec(ctx, st, w, ld, 1, A, ld, N, Linv));
@@ -1217,6 +1271,12 @@ extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, con
             mll_finish_kernel<<<1, 32, 0, st>>>(partial, tiles * tiles, nth, sc + 8);
             CUDA_TRY(ctx, cudaGetLastError());
             ctx->launches += 2;
+            if (grad_noise_vec) {
+                mll_diag_grad_kernel<<<grid_for(N), 256, 0, st>>>(alpha, Kinv, ld, N, w);   // w is free again
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches++;
+                CUDA_TRY(ctx, cudaMemcpyAsync(grad_noise_vec, w, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+            }
         }
     }
     double hsc[8 + MLL_MAX_D + 3];
@@ -1231,9 +1291,22 @@ extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, con
         *value = NAN;
         if (grad)
             for (int k = 0; k < nth; ++k) grad[k] = NAN;
+        if (grad_noise_vec)
+            for (int64_t i = 0; i < N; ++i) grad_noise_vec[i] = NAN;
     }
     ex->last.flops = (double)N * N * N * (grad ? 1.0 / 3 + 1.0 + 1.0 : 1.0 / 3);
     return B2GP_OK;
+}
+
+extern "C" int b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d, const double* theta,
+                        double jitter, unsigned flags, double* value, double* grad, double* alpha_out, int* info) {
+    return mll_impl(ctx, kind, X, N, yres, d, theta, nullptr, jitter, flags, value, grad, alpha_out, nullptr, info);
+}
+
+extern "C" int b2gp_mll_v(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d, const double* theta,
+                          const double* noise_vec, double jitter, unsigned flags, double* value, double* grad, double* alpha_out,
+                          double* grad_noise_vec, int* info) {
+    return mll_impl(ctx, kind, X, N, yres, d, theta, noise_vec, jitter, flags, value, grad, alpha_out, grad_noise_vec, info);
 }
 
 // value and gradient of the VFE bound of the sparse GP (see sparse_elbo.cuh): d/dlog(lengthscale[d], k_scale, noise, period)
@@ -1374,6 +1447,162 @@ extern "C" int b2gp_sparse_elbo(b2gp_ctx* ctx, int kind, const double* Xu, int64
     return B2GP_OK;
 }
 
+// ------------------------------------------------------------------------------------------ MVN sampling
+// y[s, i, :] = mean[s, :] + chol(cov[s]) eps[s, i, :]  -- numpyro.distributions.MultivariateNormal(mean, cov).sample
+// (call sites gpax/models/gp.py:292, gpax/models/hskgp.py via ExactGP._predict, gpax/acquisition/base_acq.py:221) for
+// covariances the caller modified after the posterior call (VarNoiseGP adds the predicted noise to the diagonal).
+extern "C" int b2gp_mvn_sample(b2gp_ctx* ctx, const double* mean, const double* cov, int64_t S, int64_t P, const double* eps,
+                               int64_t n, double* y, int* info, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, mean && cov && eps && y && info && S >= 1 && P >= 1 && n >= 1);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool dev = dev_ptrs(flags);
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const double *dmean, *dcov, *deps;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], mean, (size_t)S * P * 8, dev, &dmean));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], cov, (size_t)S * P * P * 8, dev, &dcov));
+    RET_IF(stage_in(ctx, st, ctx->d_in[2], eps, (size_t)S * n * P * 8, dev, &deps));
+    double* dy = y;
+    if (!dev) {
+        RET_IF(ensure(ctx, ctx->d_out[3], (size_t)S * n * P * 8));
+        dy = (double*)ctx->d_out[3].p;
+    }
+    const int64_t ldC = round_up(P, 8);
+    RET_IF(ensure(ctx, sl.cov, (size_t)P * ldC * 8));
+    RET_IF(ensure(ctx, sl.LinvC, (size_t)linv_bytes(P)));
+    RET_IF(ensure(ctx, ctx->d_info, (size_t)S * sizeof(int)));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, (size_t)S * sizeof(int), st));
+    double* CL = (double*)sl.cov.p;
+    dim3 g2((unsigned)ceil_div(P, 32), (unsigned)ceil_div(P, 32)), b2(32, 32);
+    for (int64_t s = 0; s < S; ++s) {
+        copy2d_kernel<<<grid_for(P * P), 256, 0, st>>>(CL, ldC, dcov + s * P * P, P, P, P);
+        RET_IF(potrf_rec(ctx, st, CL, ldC, P, (double*)sl.LinvC.p, dinfo + s, 0));
+        zero_upper_kernel<<<g2, b2, 0, st>>>(CL, ldC, P);
+        double* Y = dy + s * n * P;
+        bcast_rows_kernel<<<grid_for(n * P), 256, 0, st>>>(Y, P, n, P, dmean + s * P);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches += 3;
+        RET_IF(gemm_nt(ctx, st, n, P, P, 1.0, deps + s * n * P, P, CL, ldC, 1.0, Y, P, false));
+        nan_if_bad_kernel<<<grid_for(n * P), 256, 0, st>>>(Y, P, n, P, dinfo + s, nullptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(info, dinfo, (size_t)S * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(y, dy, (size_t)S * n * P * 8, cudaMemcpyDeviceToHost, st));
+    return tm.end(st, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------ acquisition epilogues
+// see include/b200gp.h; kernels in acq.cuh
+extern "C" int b2gp_acq_moments(b2gp_ctx* ctx, int kind, const double* mean, const double* var, int64_t R, int64_t P, int have_best,
+                                double best_f, double param, int maximize, double* out, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= ACQ_EI && kind <= ACQ_POI);
+    ARG_CHECK(ctx, var && out && R >= 1 && P >= 1);
+    ARG_CHECK(ctx, mean || kind == ACQ_UE);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool dev = dev_ptrs(flags);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const double *dmean, *dvar;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], mean, (size_t)R * P * 8, dev, &dmean));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], var, (size_t)R * P * 8, dev, &dvar));
+    double* dout = out;
+    if (!dev) {
+        RET_IF(ensure(ctx, ctx->d_out[0], (size_t)R * P * 8));
+        dout = (double*)ctx->d_out[0].p;
+    }
+    RET_IF(ensure(ctx, ctx->slots[0].misc, (size_t)(R + 16) * 8));
+    double* dbest = (double*)ctx->slots[0].misc.p;
+    if (kind == ACQ_EI || kind == ACQ_POI) {
+        if (have_best) {
+            std::vector<double> hb((size_t)R, best_f);
+            CUDA_TRY(ctx, cudaMemcpyAsync(dbest, hb.data(), (size_t)R * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        } else {
+            acq_best_kernel<<<(unsigned)R, 256, 0, st>>>(dmean, P, P, maximize, dbest);
+            ctx->launches++;
+        }
+    }
+    acq_moments_kernel<<<grid_for(R * P), 256, 0, st>>>(kind, dmean, dvar, P, R, P, dbest, param, maximize, dout, P);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, (size_t)R * P * 8, cudaMemcpyDeviceToHost, st));
+    return tm.end(st, nullptr);
+}
+
+extern "C" int b2gp_acq_samples(b2gp_ctx* ctx, int kind, const double* y, int64_t R, int64_t P, int have_best, double best_f,
+                                double param, int maximize, double* out, double* mean_out, double* var_out, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= ACQ_EI && kind <= ACQ_POI);
+    ARG_CHECK(ctx, y && out && R >= 1 && P >= 1);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool dev = dev_ptrs(flags);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const double* dy;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], y, (size_t)R * P * 8, dev, &dy));
+    RET_IF(ensure(ctx, ctx->d_out[0], (size_t)3 * P * 8));
+    double* dm = (double*)ctx->d_out[0].p;
+    double* dv = dm + P;
+    double* dout = dev ? out : dv + P;
+    RET_IF(ensure(ctx, ctx->slots[0].misc, 16 * 8));
+    double* dbest = (double*)ctx->slots[0].misc.p;
+    sample_moments_kernel<<<(unsigned)ceil_div(P, 128), 128, 0, st>>>(dy, R, P, dm, dv);
+    ctx->launches++;
+    if (kind == ACQ_EI || kind == ACQ_POI) {
+        if (have_best) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(dbest, &best_f, 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        } else {
+            acq_best_kernel<<<1, 256, 0, st>>>(dm, P, P, maximize, dbest);
+            ctx->launches++;
+        }
+    }
+    acq_moments_kernel<<<grid_for(P), 256, 0, st>>>(kind, dm, dv, P, 1, P, dbest, param, maximize, dout, P);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    const cudaMemcpyKind kd = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, (size_t)P * 8, kd, st));
+    if (mean_out) CUDA_TRY(ctx, cudaMemcpyAsync(mean_out, dm, (size_t)P * 8, kd, st));
+    if (var_out) CUDA_TRY(ctx, cudaMemcpyAsync(var_out, dv, (size_t)P * 8, kd, st));
+    return tm.end(st, nullptr);
+}
+
+extern "C" int b2gp_kg(b2gp_ctx* ctx, const double* mean, const double* cov, int64_t P, const double* ysim, int64_t n,
+                       double diag_sub, double noise_plus_jitter, int maximize, double* out, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, mean && cov && ysim && out && P >= 1 && n >= 1);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const bool dev = dev_ptrs(flags);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const double *dmean, *dcov, *dys;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], mean, (size_t)P * 8, dev, &dmean));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], cov, (size_t)P * P * 8, dev, &dcov));
+    RET_IF(stage_in(ctx, st, ctx->d_in[2], ysim, (size_t)n * P * 8, dev, &dys));
+    double* dout = out;
+    if (!dev) {
+        RET_IF(ensure(ctx, ctx->d_out[0], (size_t)P * 8));
+        dout = (double*)ctx->d_out[0].p;
+    }
+    RET_IF(ensure(ctx, ctx->slots[0].misc, 16 * 8));
+    double* dbest = (double*)ctx->slots[0].misc.p;
+    acq_best_kernel<<<1, 256, 0, st>>>(dmean, P, P, maximize, dbest);
+    kg_kernel<<<(unsigned)P, 256, 0, st>>>(dmean, dcov, P, dys, (int)n, P, diag_sub, noise_plus_jitter, maximize, dbest, dout);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    if (!dev) CUDA_TRY(ctx, cudaMemcpyAsync(out, dout, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    return tm.end(st, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------ debug
 // Development aid (not part of include/b200gp.h): run the leaf kernel on a device block with per-phase
 // clock64 / globaltimer stamps.  prof_host receives 2*16 values (cycles, ns) per stamp.
@@ -1460,5 +1689,32 @@ extern "C" int b2gp_debug_ozaki(b2gp_ctx* ctx, int S, int64_t m, int64_t n, int6
                             "for TMEM drain %.0f; tiles %.0f, k-blocks/tile %lld\n",
                     w / t, e / t, u / t, mt / t, mf / t, me / t, t, (long long)((k + 31) / 32));
     }
+    return B2GP_OK;
+}
+
+// Development aid / roofline denominator: the measured int8 tcgen05 ceiling in TOP/s (see oz_i8_peak_kernel), best of `reps`.
+extern "C" int b2gp_debug_i8_peak(b2gp_ctx* ctx, int iters, int reps, double* tops_out, double* ms_out) {
+    if (!ctx || !tops_out || iters < 4 || reps < 1) return B2GP_ERR_ARG;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->slots[0].stream;
+    const int smem = 200 * 1024;   // one CTA per SM
+    static PerDeviceOnce attr;
+    if (attr.need(ctx->device)) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(oz_i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr.done(ctx->device);
+    }
+    double best = 1e30;
+    for (int r = 0; r < reps + 1; ++r) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st));
+        oz_i8_peak_kernel<<<ctx->sm_count, 128, smem, st>>>(iters, nullptr);
+        CUDA_TRY(ctx, cudaGetLastError());
+        CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st));
+        CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev_b));
+        float ms = 0.f;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+        if (r > 0 && ms < best) best = ms;
+    }
+    *tops_out = 2.0 * 128 * 256 * 32 * (double)iters * ctx->sm_count / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
     return B2GP_OK;
 }

@@ -429,6 +429,52 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- peak probe
+// The int8 tensor-pipe ceiling, measured instead of assumed: every CTA (one per SM) issues `iters` back-to-back
+// tcgen05.mma kind::i8 M128 N256 K32 on operands that stay in shared memory (no TMA, no epilogue), alternating between
+// the two halves of TMEM, then one commit.  ops = 2 * 128 * 256 * 32 per instruction.  What oz_mma_kernel can reach at
+// most; its roofline denominator in bench.py.
+__global__ void __launch_bounds__(128, 1) oz_i8_peak_kernel(int iters, int* sink) {
+    extern __shared__ uint8_t pk_raw[];
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(pk_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bar = base + 4096 + 8192;
+    const uint32_t slot = bar + 16;
+    uint8_t* gen = pk_raw + (base - raw);
+    for (int i = threadIdx.x; i < (4096 + 8192) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(gen)[i] = 0x01010101u * (uint32_t)(i & 3);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the operands -> async proxy (MMA)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + 4096 + 8192 + 16);
+    if (threadIdx.x == 0) {
+        constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24) | ((uint32_t)(256 >> 3) << 17);
+        const uint64_t ad = oz_smem_desc(base), bd = oz_smem_desc(base + 4096);
+        for (int i = 0; i < iters; ++i) tc_mma_i8(tmem + 256u * (uint32_t)(i & 1), ad, bd, IDESC, i >= 2 ? 1u : 0u);
+        tc_commit(bar);
+        mbar_wait(bar, 0);
+        tc_fence_after();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v[16];
+        tc_ld16(tmem + ((uint32_t)0 << 16), v);
+        tc_wait_ld();
+        if (sink && v[0] == 0x7fffffff) sink[0] = v[1];   // keeps the accumulators observable
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 static bool make_tmap_u8(CUtensorMap* map, const int8_t* base, int64_t rows_total, int64_t kpad, int box_rows) {
     PFN_tmapEncodeTiled enc = tmap_encoder();

@@ -264,7 +264,7 @@ def _nuts_draw(lj, u0, lp0, g0, eps, rng, minv, max_depth=10):
         if ok2 and math.log(rng.uniform()) < lw2 - lw_tot:
             uc, lpc, gc = b[6], b[7], b[8]
         span = up_ - um_
-        ok = ok2 and np.dot(span, rm_) >= 0 and np.dot(span, rp_) >= 0
+        ok = ok2 and np.dot(span, minv * rm_) >= 0 and np.dot(span, minv * rp_) >= 0     # U-turn in the metric's velocity
         return um_, rm_, gm_, up_, rp_, gp_, uc, lpc, gc, lw_tot, ok
 
     while depth < max_depth:
@@ -280,16 +280,22 @@ def _nuts_draw(lj, u0, lp0, g0, eps, rng, minv, max_depth=10):
             u, lp, g = t[6], t[7], t[8]
         logw = np.logaddexp(logw, lw2)
         span = up - um
-        if not ok or np.dot(span, rm) < 0 or np.dot(span, rp) < 0:
+        if not ok or np.dot(span, minv * rm) < 0 or np.dot(span, minv * rp) < 0:
             break
         depth += 1
     return u, lp, g, alpha_sum / max(n_alpha, 1), depth, diverged
 
 
 def fit_exact_gp(model, rng_key, num_warmup, num_samples, num_chains, progress_bar, **kwargs):
-    """gp.py:207-218: NUTS with dual-averaging step-size adaptation (target accept 0.8) and a diagonal mass matrix
-    estimated over the second half of warm-up; chains run one after another ('sequential')."""
-    lj = LogJoint(model, kwargs.get("jitter", 1e-6))
+    """gp.py:207-218."""
+    return run_nuts(LogJoint(model, kwargs.get("jitter", 1e-6)), rng_key, num_warmup, num_samples, num_chains, progress_bar)
+
+
+def run_nuts(lj, rng_key, num_warmup, num_samples, num_chains, progress_bar):
+    """NUTS over any log joint `lj(u, jacobian) -> (value, grad)` with `dim`, `init_u()`, `to_dict(U)`.  Dual-averaging
+    step-size adaptation (target accept 0.8).  Warm-up windows as in Stan / NumPyro: draws of the middle of warm-up
+    estimate a diagonal mass matrix, which is installed at 3/4 of warm-up; the step size is then re-initialised for the
+    new metric and dual averaging restarts over the last quarter.  Chains run one after another ('sequential')."""
     root = seed_from_key(rng_key)
     chains, stats = [], []
     for c in range(int(num_chains)):
@@ -299,23 +305,26 @@ def fit_exact_gp(model, rng_key, num_warmup, num_samples, num_chains, progress_b
         minv = np.ones(lj.dim)
         eps = _find_eps(lj, u, lp, g, rng, minv)
         mu, hbar, log_eps_bar, gamma, t0, kappa, delta = math.log(10 * eps), 0.0, 0.0, 0.05, 10.0, 0.75, 0.8
-        draws, warm_buf, div = [], [], 0
+        draws, warm_buf, div, m = [], [], 0, 0
+        metric_at = (3 * int(num_warmup)) // 4 if num_warmup >= 40 else -1
         for it in range(int(num_warmup) + int(num_samples)):
             u, lp, g, acc, depth, dv = _nuts_draw(lj, u, lp, g, eps, rng, minv)
             if it < num_warmup:
-                m = it + 1
+                m += 1
                 hbar = (1 - 1 / (m + t0)) * hbar + (delta - acc) / (m + t0)
                 log_eps = mu - math.sqrt(m) / gamma * hbar
                 eta = m ** (-kappa)
                 log_eps_bar = eta * log_eps + (1 - eta) * log_eps_bar
                 eps = math.exp(log_eps)
-                if it >= num_warmup // 2:
+                if num_warmup // 4 <= it < metric_at:
                     warm_buf.append(u.copy())
+                if it == metric_at - 1 and len(warm_buf) >= 10:
+                    var = np.var(np.array(warm_buf), axis=0)
+                    minv = (len(warm_buf) * var + 1e-3 * 5) / (len(warm_buf) + 5)        # regularised, as Stan
+                    eps = _find_eps(lj, u, lp, g, rng, minv)                              # step size for the new metric
+                    mu, hbar, log_eps_bar, m = math.log(10 * eps), 0.0, 0.0, 0            # dual averaging restarts
                 if it == num_warmup - 1:
-                    if len(warm_buf) >= 20:
-                        var = np.var(np.array(warm_buf), axis=0)
-                        minv = (len(warm_buf) * var + 1e-3 * 5) / (len(warm_buf) + 5)    # regularised, as Stan
-                    eps = math.exp(log_eps_bar)
+                    eps = math.exp(log_eps_bar) if m > 0 else eps
             else:
                 draws.append(u.copy())
                 div += int(dv)

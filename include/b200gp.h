@@ -150,6 +150,23 @@ int  b2gp_posterior(b2gp_ctx* ctx, int kind,
                     const double* eps, int64_t n_samp, double* y_sampled,
                     int* info, b2gp_timing* timing);
 
+/* The same posterior with everything that may differ between the S members of the batch:
+ *   Xtr[S, xtr_stride] / Xnew[S, xnew_stride]   per-member training / test inputs (stride in doubles; 0 = shared [N,d] / [P,d]):
+ *       the outer task axis of vExactGP (gpax/models/vgp.py:125-172) and the per-draw perturbed inputs X_prime of
+ *       UIGP (gpax/models/uigp.py:131-150)
+ *   noise_vec[N] or [S, noise_vec_stride]       per-point noise variances added to the diagonal of k_XX on top of
+ *       theta's scalar noise: MeasuredNoiseGP (k + diag(measured_noise), gpax/models/mngp.py:92-97) and VarNoiseGP
+ *       (k + diag(exp(log_var)), gpax/models/hskgp.py:143-148); NULL = none.
+ * All other arguments as b2gp_posterior.                                                                          */
+int  b2gp_posterior_batch(b2gp_ctx* ctx, int kind,
+                          const double* Xtr, int64_t xtr_stride, int64_t N, const double* yres, int64_t yres_stride,
+                          const double* Xnew, int64_t xnew_stride, int64_t P, int d, int64_t S,
+                          const double* theta, const double* noise_vec, int64_t noise_vec_stride,
+                          int noiseless, double jitter, unsigned flags,
+                          double* mean, double* var, double* cov,
+                          const double* eps, int64_t n_samp, double* y_sampled,
+                          int* info, b2gp_timing* timing);
+
 /* Nystrom / VFE sparse posterior for one theta -- replaces viSparseGP.get_mvn_posterior
  * (gpax/models/sparse_gp.py:173-223).  Xu[M,d] inducing points; theta[d+3] as above;
  * outputs mean[P] and var[P] (B2GP_OUT_VAR) and/or cov[P,P] (B2GP_OUT_COV).                        */
@@ -170,6 +187,13 @@ int  b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double*
               const double* theta, double jitter, unsigned flags,
               double* value, double* grad, double* alpha_out, int* info);
 
+/* b2gp_mll with a vector of per-point noise variances on the diagonal, K = kernel(X, X, theta, noise, jitter) + diag(noise_vec)
+ * (the likelihoods of gpax/models/mngp.py:92-97 and gpax/models/hskgp.py:143-148), and grad_noise_vec[N] (HOST, optional,
+ * needs grad) = d value / d noise_vec[i] = 1/2 (alpha_i^2 - K^{-1}_ii).                                              */
+int  b2gp_mll_v(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double* yres, int d,
+                const double* theta, const double* noise_vec, double jitter, unsigned flags,
+                double* value, double* grad, double* alpha_out, double* grad_noise_vec, int* info);
+
 /* Fit side of the sparse GP: the VFE bound of viSparseGP.model (gpax/models/sparse_gp.py:62-114)
  *   log LowRankMVN(yres; 0, W^T W + noise I) - 1/2 clip(sum_n (Kff_nn - Qff_nn) / noise, 0),  W = Luu^{-1} K(Xu, X)
  * and its gradient w.r.t. (log lengthscale[d], log k_scale, log noise, log period) in grad_theta[d+3] and w.r.t. the
@@ -178,6 +202,34 @@ int  b2gp_mll(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const double*
 int  b2gp_sparse_elbo(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* X, int64_t N,
                       const double* yres, int d, const double* theta, double jitter, unsigned flags,
                       double* value, double* grad_theta, double* grad_Xu, int* info);
+
+/* Samples of S multivariate normals: y[s,i,:] = mean[s,:] + chol(cov[s]) eps[s,i,:], i < n -- replaces
+ * numpyro.distributions.MultivariateNormal(mean, cov).sample (gpax/models/gp.py:292, gpax/acquisition/base_acq.py:221)
+ * where the caller changed cov after the posterior call (gpax/models/hskgp.py:201-204 adds the predicted noise variance).
+ * info[s] = 0 or the first bad pivot of cov[s] (that member's samples are NaN).                                    */
+int  b2gp_mvn_sample(b2gp_ctx* ctx, const double* mean, const double* cov, int64_t S, int64_t P,
+                     const double* eps, int64_t n, double* y, int* info, unsigned flags);
+
+/* ---- acquisition epilogues on the posterior's outputs, host or device pointers ----------
+ * kind: 0 EI, 1 UCB, 2 UE, 3 POI -- gpax/acquisition/base_acq.py:20-71 (ei), 74-104 (ucb), 107-130 (ue), 133-155 (poi).
+ *   mean[R,P], var[R,P] -> out[R,P]; row r is one posterior (R = 1 for viGP / the pooled moments of an MCMC model,
+ *   R = number of sub-sampled draws for the q-batch functions, gpax/acquisition/batch_acquisition.py:110-116).
+ *   have_best = 0: best_f is derived from each row's mean (max when maximize, else min: base_acq.py:59-60);
+ *   param = beta (UCB) or xi (POI).                                                                             */
+int  b2gp_acq_moments(b2gp_ctx* ctx, int kind, const double* mean, const double* var, int64_t R, int64_t P,
+                      int have_best, double best_f, double param, int maximize, double* out, unsigned flags);
+/* Same, from posterior samples y[R,P] (R = S*n rows of y_sampled): column mean and population variance
+ * (gpax/acquisition/acquisition.py:31-34), then the acquisition function.  mean_out / var_out [P] optional.      */
+int  b2gp_acq_samples(b2gp_ctx* ctx, int kind, const double* y, int64_t R, int64_t P,
+                      int have_best, double best_f, double param, int maximize,
+                      double* out, double* mean_out, double* var_out, unsigned flags);
+/* Knowledge gradient (gpax/acquisition/base_acq.py:158-232) from one posterior: mean[P], cov[P,P] of the candidates,
+ * ysim[n,P] simulated observations (base_acq.py:223).  The reference re-inverts the (N+1)x(N+1) training covariance
+ * for every candidate and simulation; here the rank-1 (block-inverse) update of the posterior mean is evaluated in
+ * closed form.  diag_sub = noise_p + jitter (what `cov` carries on its diagonal beyond the latent covariance),
+ * noise_plus_jitter = the diagonal term of the appended training point.  out[P].                                 */
+int  b2gp_kg(b2gp_ctx* ctx, const double* mean, const double* cov, int64_t P, const double* ysim, int64_t n,
+             double diag_sub, double noise_plus_jitter, int maximize, double* out, unsigned flags);
 
 /* ---- multi-GPU building blocks.  One process per GPU; the exchange steps
  * (panel broadcast, M x M all-reduce) are issued by the host side over NCCL on these same device

@@ -1,0 +1,214 @@
+"""GPU: the SURVEY.md section 8f rows -- model variants (8f-3) and acquisition epilogues (8f-4) -- through the C-ABI and the
+Python shell, against the golden vectors made by the reference's own source (tests/golden/make_golden_f.py) and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import ROOT, assert_close
+from oracle import acq_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gf():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors_f.npz"))
+
+
+@pytest.fixture(scope="module")
+def gp():
+    import gpax_b200
+    return gpax_b200
+
+
+# ------------------------------------------------------------------ 8f-4 acquisition epilogues
+def test_base_acquisition_golden(gp, gf):
+    from gpax_b200 import acquisition as acq
+    mean, var = gf["acq_mean"], gf["acq_var"]
+    for mx in (False, True):
+        for bf, tag in ((None, "none"), (0.3, "given")):
+            np.testing.assert_allclose(acq.ei((mean, var), bf, mx), gf[f"acq_ei_mx{int(mx)}_bf{tag}"], rtol=1e-11, atol=1e-300)
+            np.testing.assert_allclose(acq.poi((mean, var), bf, 0.01, mx), gf[f"acq_poi_mx{int(mx)}_bf{tag}"], rtol=1e-11, atol=1e-300)
+        np.testing.assert_allclose(acq.ucb((mean, var), 0.25, mx), gf[f"acq_ucb_mx{int(mx)}"], rtol=1e-14)
+    np.testing.assert_allclose(acq.ue((mean, var)), gf["acq_ue"], rtol=1e-15)
+
+
+def test_acquisition_rows_and_sample_moments(gp):
+    """[R, P] rows with a per-row best (the q-batch form, batch_acquisition.py:110-116) and the moment reduction over
+    posterior samples (acquisition.py:31-34) at a realistic size"""
+    ctx = gp.default_context()
+    rng = np.random.default_rng(5)
+    R, P = 7, 3001
+    mean, var = rng.standard_normal((R, P)), np.exp(rng.normal(-1, 1, (R, P)))
+    got = ctx.acq_moments("EI", mean, var, None, 0.0, True)
+    ref = np.stack([ao.ei(mean[r], var[r], None, True) for r in range(R)])
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-300)
+    y = rng.standard_normal((40, P)) * 0.3 + rng.standard_normal(P)
+    rm, rv = ao.moments_from_samples(y)
+    refs = {"EI": ao.ei(rm, rv, None, False), "UCB": ao.ucb(rm, rv, 0.5, False), "POI": ao.poi(rm, rv, None, 0.02, False),
+            "UE": ao.ue(rm, rv)}
+    for kind, param in (("EI", 0.0), ("UCB", 0.5), ("POI", 0.02), ("UE", 0.0)):
+        a, m, v = ctx.acq_samples(kind, y, None, param, False)
+        np.testing.assert_allclose(m, rm, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(v, rv, rtol=1e-12)
+        np.testing.assert_allclose(a, refs[kind], rtol=1e-9, atol=1e-300)
+
+
+@pytest.mark.parametrize("kname", ["RBF", "Matern"])
+def test_knowledge_gradient_golden(gp, gf, kname):
+    """closed-form rank-1 update (b2gp_kg) against the reference's literal re-inversion per candidate and simulation"""
+    from gpax_b200 import acquisition as acq
+    params = {"k_length": np.array([0.4, 0.5]), "k_scale": 1.3, "noise": 0.05}
+    m = gp.ExactGP(2, kname)
+    m.X_train, m.y_train = gf["kg_Xtr"], gf["kg_ytr"]
+    for mx in (True, False):
+        for nl in (True, False):
+            v = acq.kg(m, gf["kg_Xc"], params, None, n=5, maximize=mx, noiseless=nl, eps=gf["kg_eps"])
+            assert_close(v, gf[f"kg_{kname}_mx{int(mx)}_nl{int(nl)}"], 1e-7, f"kg {kname} maximize={mx} noiseless={nl}")
+
+
+def test_knowledge_gradient_vs_literal_oracle_larger(gp):
+    from gpax_b200 import acquisition as acq
+    rng = np.random.default_rng(8)
+    N, P, n = 300, 40, 4
+    X = rng.uniform(0, 1, (N, 2))
+    y = np.sin(6 * X[:, 0]) * X[:, 1] + 0.05 * rng.standard_normal(N)
+    Xc = rng.uniform(0, 1, (P, 2))
+    params = {"k_length": np.array([0.3, 0.3]), "k_scale": 1.0, "noise": 0.05}
+    eps = rng.standard_normal((n, P))
+    m = gp.ExactGP(2, "Matern")
+    m.X_train, m.y_train = X, y
+    got = acq.kg(m, Xc, params, None, n=n, maximize=True, noiseless=True, eps=eps)
+    ref = ao.kg(X, y, Xc, params, "Matern", eps, True, True)
+    assert_close(got, ref, 1e-7, "kg N=300")
+
+
+def test_model_level_acquisition_wiring(gp):
+    """EI / UCB / UE / POI through a viGP-style model (moments) and an MCMC-style model (sample moments); penalties"""
+    from gpax_b200 import acquisition as acq
+    rng = np.random.default_rng(2)
+    X = rng.uniform(0, 1, (200, 1))
+    y = np.sin(7 * X[:, 0]) + 0.05 * rng.standard_normal(200)
+    Xn = np.linspace(0, 1, 64)[:, None]
+    v = gp.viGP(1, "RBF")
+    v.X_train, v.y_train = X, y
+    v.kernel_params = {"k_length": np.array([0.2]), "k_scale": 1.0, "noise": 0.01}
+    mean, var = v.predict(None, Xn)
+    np.testing.assert_allclose(acq.EI(None, v, Xn, maximize=True), ao.ei(mean, var, None, True), rtol=1e-9, atol=1e-300)
+    np.testing.assert_allclose(acq.UCB(None, v, Xn, beta=4.0), ao.ucb(mean, var, 4.0, False), rtol=1e-12)
+    pen = acq.UE(None, v, Xn, penalty="inverse_distance", recent_points=Xn[:3], penalty_factor=2.0)
+    assert pen.shape == (64,) and (pen < ao.ue(mean, var)).all()
+    with pytest.raises(ValueError):
+        acq.EI(None, v, Xn, penalty="delta")
+
+    class FakeMCMC:
+        def get_samples(self, group_by_chain=False):
+            return {"k_length": np.full((6, 1), 0.2), "k_scale": np.ones(6), "noise": np.full(6, 0.01)}
+    m = gp.ExactGP(1, "RBF")
+    m.X_train, m.y_train, m.mcmc = X, y, FakeMCMC()
+    a = acq.POI(3, m, Xn, n=5, maximize=True)
+    _, ys = m.predict(3, Xn, n=5)
+    rm, rv = ao.moments_from_samples(ys.reshape(-1, 64))
+    np.testing.assert_allclose(a, ao.poi(rm, rv, None, 0.01, True), rtol=1e-8, atol=1e-12)
+    q = acq.qEI(3, m, Xn, subsample_size=3)
+    assert q.shape == (3, 64) and np.isfinite(q).all()
+    k = acq.KG(3, m, Xn[:16], n=2)
+    assert k.shape == (6, 16) and np.isfinite(k).all()
+
+
+# ------------------------------------------------------------------ 8f-3 model variants
+def test_var_noise_gp_golden(gp, gf):
+    params = {"k_length": np.array([0.3]), "k_scale": 1.1, "k_noise_length": np.array([0.5]), "k_noise_scale": 0.7,
+              "log_var": gf["hsk_log_var"], "noise": 0.0}
+    m = gp.VarNoiseGP(1, kernel="RBF", noise_kernel="Matern")
+    m.X_train, m.y_train = gf["hsk_Xtr"], gf["hsk_ytr"]
+    mean, cov = m.get_mvn_posterior(gf["hsk_Xte"], params)
+    # k_XX carries jitter only here (hskgp.py:178: noise 0), cond(K) ~ 1e7: the reference's LU inverse is the loose side
+    assert_close(mean, gf["hsk_mean"], 1e-6, "VarNoiseGP mean")
+    assert_close(cov, gf["hsk_cov"], 1e-6, "VarNoiseGP cov")
+    samples = {k: np.stack([np.asarray(v)] * 3) for k, v in params.items()}
+    ym, ys = m.predict(0, gf["hsk_Xte"], samples, n=2)
+    assert ym.shape == (15,) and ys.shape == (3, 2, 15) and np.isfinite(ys).all()
+
+
+def test_task_batch_golden(gp, gf):
+    params = {k: gf["vgp_" + k] for k in ("k_length", "k_scale", "noise")}
+    m = gp.vExactGP(2, "Matern")
+    m.X_train, m.y_train = gf["vgp_Xtr"], gf["vgp_ytr"]
+    mean, cov = m.get_mvn_posterior(gf["vgp_Xte"], params)
+    assert_close(mean, gf["vgp_mean"], 1e-9, "vExactGP mean")
+    assert_close(cov, gf["vgp_cov"], 1e-9, "vExactGP cov")
+    samples = {k: np.stack([v, v * 1.05]) for k, v in params.items()}
+    ym, ys = m.predict(1, gf["vgp_Xte"], samples, n=3)
+    assert ym.shape == (3, 11) and ys.shape == (2, 3, 3, 11) and np.isfinite(ys).all()
+
+
+def test_uigp_golden(gp, gf):
+    params = {"k_length": np.array([0.35]), "k_scale": 0.9, "noise": 0.04, "X_prime": gf["uigp_Xprime"]}
+    m = gp.UIGP(1, "RBF", sigma_x_prior_dist=object())
+    m.X_train, m.y_train = gf["uigp_Xtr"], gf["uigp_ytr"]
+    mean, cov = m.get_mvn_posterior(gf["uigp_Xte"], params, noiseless=True)
+    assert_close(mean, gf["uigp_mean"], 1e-9, "UIGP mean")
+    assert_close(cov, gf["uigp_cov"], 1e-9, "UIGP cov")
+
+
+def test_noise_vector_posterior_and_likelihood(gp, gf):
+    """per-point noise variances on k_XX's diagonal (mngp.py:92-97 / hskgp.py:143-148) through b2gp_posterior_batch and
+    b2gp_mll_v: value against the golden log density, gradients against central differences, posterior against NumPy"""
+    ctx = gp.default_context()
+    X, y, nv = gf["mn_Xtr"], gf["mn_ytr"], gf["mn_noise"]
+    th = np.array([0.4, 1.2, 0.0, 1.0])
+    val, g, alpha, info, gnv = ctx.mll("RBF", X, y, th, 1e-6, True, True, nv)
+    assert info == 0
+    np.testing.assert_allclose(val, gf["mn_logp"], rtol=1e-10)
+    K = gf["mn_cov"]
+    np.testing.assert_allclose(alpha, np.linalg.solve(K, y), rtol=1e-7)
+    Kinv = np.linalg.inv(K)
+    np.testing.assert_allclose(gnv, 0.5 * (alpha ** 2 - np.diag(Kinv)), rtol=1e-6, atol=1e-8)
+    for k, h in ((0, 1e-5), (1, 1e-5)):
+        tp, tm = th.copy(), th.copy()
+        tp[k] *= np.exp(h)
+        tm[k] *= np.exp(-h)
+        fd = (ctx.mll("RBF", X, y, tp, 1e-6, False, False, nv)[0] - ctx.mll("RBF", X, y, tm, 1e-6, False, False, nv)[0]) / (2 * h)
+        np.testing.assert_allclose(g[k], fd, rtol=1e-5)
+    Xn = np.linspace(0, 1, 9)[:, None]
+    out = ctx.posterior("RBF", X, y, Xn, th[None], True, 1e-6, ("mean", "cov"), noise_vec=nv)
+    prm = {"k_length": np.array([0.4]), "k_scale": 1.2}
+    kpx = oracle.rbf_kernel(Xn, X, prm, jitter=0.0)
+    kpp = oracle.rbf_kernel(Xn, Xn, prm, 0.0, jitter=1e-6)
+    assert_close(out["mean"][0], kpx @ (Kinv @ y), 1e-8, "noise-vector posterior mean")
+    assert_close(out["cov"][0], kpp - kpx @ Kinv @ kpx.T, 1e-8, "noise-vector posterior cov")
+
+
+def test_measured_noise_gp_predict(gp):
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 1, (80, 1))
+    y = np.sin(5 * X[:, 0]) + 0.05 * rng.standard_normal(80)
+    mnoise = 0.01 + 0.02 * X[:, 0]
+    m = gp.MeasuredNoiseGP(1, "Matern")
+    m.X_train, m.y_train, m.measured_noise = X, y, mnoise
+    samples = {"k_length": np.full((4, 1), 0.3), "k_scale": np.ones(4), "noise": np.zeros(4)}
+    Xn = np.linspace(0, 1, 21)[:, None]
+    ym, ys = m.predict(0, Xn, samples, n=3)
+    assert ym.shape == (21,) and ys.shape == (4, 3, 21) and np.isfinite(ys).all()
+    np.testing.assert_allclose(m.noise_predicted, 0.01 + 0.02 * Xn[:, 0], rtol=1e-9)    # the linear extrapolation of the noise
+
+
+def test_variant_fits_run(gp):
+    """MeasuredNoiseGP.fit and VarNoiseGP.fit: short NUTS runs on the GPU likelihoods recover sensible parameters"""
+    rng = np.random.default_rng(4)
+    X = np.sort(rng.uniform(0, 1, 60))[:, None]
+    f = np.sin(6 * X[:, 0])
+    noise_sd = 0.05 + 0.25 * X[:, 0]
+    y = f + noise_sd * rng.standard_normal(60)
+    m = gp.MeasuredNoiseGP(1, "RBF")
+    m.fit(0, X, y, noise_sd ** 2, num_warmup=60, num_samples=40, progress_bar=False, print_summary=False)
+    s = m.get_samples()
+    assert s["k_length"].shape == (40, 1) and (s["noise"] == 0).all() and 0.05 < np.median(s["k_length"]) < 1.0
+    h = gp.VarNoiseGP(1, "RBF", noise_kernel="RBF")
+    h.fit(1, X, y, num_warmup=60, num_samples=30, progress_bar=False, print_summary=False)
+    dv = h.get_data_var_samples()
+    assert dv.shape == (30, 60) and np.isfinite(dv).all()
+    assert np.median(dv[:, 45:]) > np.median(dv[:, :15])            # the inferred noise grows with x, as the data's does
