@@ -61,11 +61,13 @@ struct OzArgs {
 // the reads are strided)
 template <int S>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ A, int64_t lda, int rows, int k, int8_t* __restrict__ planes,
-                                                       int rows_pad, int kpad, double* __restrict__ scale, int trans) {
+                                                       int rows_pad, int kpad, double* __restrict__ scale, int trans,
+                                                       const int64_t* __restrict__ rowmap128) {
     __shared__ double red[8];
     const int row = blockIdx.x;
     const int tid = threadIdx.x;
     const int64_t sr = trans ? 1 : lda, sk = trans ? lda : 1;   // strides of (row, kk)
+    if (rowmap128) A += (rowmap128[row >> 7] - (int64_t)(row & ~127)) * lda;   // source row = rowmap128[row / 128] + row % 128
     int e = 0;
     if (row < rows) {
         double mx = 0.0;
@@ -495,42 +497,89 @@ static bool make_tmap_u8(CUtensorMap* map, const int8_t* base, int64_t rows_tota
 struct OzMode {
     bool overwrite = false, transB = false, ktri = false;
 };
+// One sliced operand: S digit planes [S][rows_pad][kpad] + the row scales.
+struct OzOperand {
+    const int8_t* planes = nullptr;
+    const double* scale = nullptr;
+    int64_t rows_pad = 0;
+};
+
+// slice `rows` rows of length k (source row r at src + rowmap128[r / 128] * ld + (r % 128) * ld when a row map is given -- a
+// device array with one source row index per group of 128 rows, for operands gathered from block-cyclic storage --
+// else at src + r * ld) into `planes` / `scale` (capacity checked by the caller)
 template <int S>
-static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
-                         int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only, OzMode mode = OzMode()) {
-    if (m <= 0 || n <= 0 || k <= 0) return B2GP_OK;
-    if (k > OZ_K_MAX) return B2GP_ERR_UNSUPPORTED;  // int32 accumulation bound (the dispatcher splits longer k)
-    const int64_t kpad = round_up(k, OZ_KB);
-    const int64_t ra = round_up(m, 128), rb = round_up(n, 128);
-    const bool same = (A == B && lda == ldb && n <= m && !mode.transB);   // B's rows are the first n rows of A: one set of planes
-    RET_IF(ensure(ctx, w.planesA, (size_t)S * ra * kpad));
-    RET_IF(ensure(ctx, w.scaleA, (size_t)ra * 8));
-    oz_slice_kernel<S><<<(unsigned)ra, 256, 0, st>>>(A, lda, (int)m, (int)k, (int8_t*)w.planesA.p, (int)ra, (int)kpad, (double*)w.scaleA.p, 0);
-    const int8_t* pb = (const int8_t*)w.planesA.p;
-    const double* sb = (const double*)w.scaleA.p;
-    int64_t rbp = ra;
-    if (!same) {
-        RET_IF(ensure(ctx, w.planesB, (size_t)S * rb * kpad));
-        RET_IF(ensure(ctx, w.scaleB, (size_t)rb * 8));
-        oz_slice_kernel<S><<<(unsigned)rb, 256, 0, st>>>(B, ldb, (int)n, (int)k, (int8_t*)w.planesB.p, (int)rb, (int)kpad, (double*)w.scaleB.p,
-                                                         mode.transB ? 1 : 0);
-        pb = (const int8_t*)w.planesB.p;
-        sb = (const double*)w.scaleB.p;
-        rbp = rb;
-    }
+static int oz_slice_launch(b2gp_ctx* ctx, cudaStream_t st, const double* src, int64_t ld, int64_t rows, int64_t k, DevBuf& planes,
+                           DevBuf& scale, bool trans, const int64_t* rowmap128, OzOperand* out) {
+    const int64_t kpad = round_up(k, OZ_KB), rp = round_up(rows, 128);
+    RET_IF(ensure(ctx, planes, (size_t)S * rp * kpad));
+    RET_IF(ensure(ctx, scale, (size_t)rp * 8));
+    oz_slice_kernel<S><<<(unsigned)rp, 256, 0, st>>>(src, ld, (int)rows, (int)k, (int8_t*)planes.p, (int)rp, (int)kpad, (double*)scale.p,
+                                                     trans ? 1 : 0, rowmap128);
     CUDA_TRY(ctx, cudaGetLastError());
-    ctx->launches += same ? 1 : 2;
+    ctx->launches++;
+    out->planes = (const int8_t*)planes.p;
+    out->scale = (const double*)scale.p;
+    out->rows_pad = rp;
+    return B2GP_OK;
+}
+
+// the band-ordered tile list of an m x n (lower-only / trapezoid) product, cached per shape in `w`
+static int oz_default_list(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int tiles_m, int tiles_n, bool lower_only, int CL,
+                           const int2** list, int64_t* count) {
+    // Tile order.  One round of the persistent loop runs sm_count consecutive list entries concurrently and, tiles
+    // being equally long, in k-lockstep: if those tiles form a compact block of (row block, column block) pairs, each
+    // operand block is fetched from HBM once per round and served to the other tiles from L2.  Bands of G row blocks,
+    // column-major inside a band: a round covers ~G x (sm_count/G) tiles = G + sm_count/G distinct operand blocks.
+    const int pairs_n = (tiles_n + CL - 1) / CL;   // list entries per row block: column tiles (CL = 1) or pairs of them
+    OzTileList* tl = nullptr;
+    for (auto& l : w.lists)
+        if (l.tm == tiles_m && l.tn == tiles_n && l.lower == (lower_only ? 1 : 0) && l.cl == CL) tl = &l;
+    if (!tl) {
+        // one factorisation cycles through ~2 N / panel distinct shapes; they repeat from draw to draw
+        tl = &w.lists[w.next_list];
+        w.next_list = (w.next_list + 1) % OZ_LISTS;
+        tl->host.clear();
+        const int G = 8;
+        for (int b0 = 0; b0 < tiles_m; b0 += G) {
+            const int b1 = b0 + G < tiles_m ? b0 + G : tiles_m;
+            // lower: row block ti owns column tiles 0 .. 2 ti + 1, i.e. pairs 0 .. ti
+            const int last = lower_only ? (CL == 2 ? b1 - 1 : 2 * (b1 - 1) + 1) : pairs_n - 1;
+            const int jmax = last < pairs_n - 1 ? last : pairs_n - 1;
+            for (int tj = 0; tj <= jmax; ++tj)
+                for (int ti = b0; ti < b1; ++ti)
+                    if (!lower_only || tj <= (CL == 2 ? ti : 2 * ti + 1)) tl->host.push_back(make_int2(ti, tj));
+        }
+        tl->tm = tiles_m;
+        tl->tn = tiles_n;
+        tl->lower = lower_only ? 1 : 0;
+        tl->cl = CL;
+        tl->count = (int64_t)tl->host.size();
+        // a list may still be in use by a kernel queued earlier on this stream: the copy is stream-ordered behind it
+        RET_IF(ensure(ctx, tl->dev, tl->host.size() * sizeof(int2)));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tl->dev.p, tl->host.data(), tl->host.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    }
+    *list = (const int2*)tl->dev.p;
+    *count = tl->count;
+    return B2GP_OK;
+}
+
+// C[m,n] (+)= alpha A B^T from sliced operands.  `list` (device, `count` entries of (row tile, column pair / tile)) overrides
+// the default tile order: the distributed factorisation passes the staircase of a block-cyclic trailing matrix.
+template <int S>
+static int oz_mma_launch(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n,
+                         int64_t k, double alpha, double* C, int64_t ldc, bool lower_only, OzMode mode, const int2* list, int64_t count) {
+    const int64_t kpad = round_up(k, OZ_KB);
     CUtensorMap mapA, mapB;
-    if (!make_tmap_u8(&mapA, (const int8_t*)w.planesA.p, (int64_t)S * ra, kpad, OZ_BM) || !make_tmap_u8(&mapB, pb, (int64_t)S * rbp, kpad, OZ_BN))
+    if (!make_tmap_u8(&mapA, oa.planes, (int64_t)S * oa.rows_pad, kpad, OZ_BM) || !make_tmap_u8(&mapB, ob.planes, (int64_t)S * ob.rows_pad, kpad, OZ_BN))
         return B2GP_ERR_UNSUPPORTED;
     OzArgs a;
     a.m = (int)m;
     a.n = (int)n;
     a.kb_count = (int)(kpad / OZ_KB);
-    a.rowsA_pad = (int)ra;
-    a.rowsB_pad = (int)rbp;
-    a.sa = (const double*)w.scaleA.p;
-    a.sb = sb;
+    a.rowsA_pad = (int)oa.rows_pad;
+    a.rowsB_pad = (int)ob.rows_pad;
+    a.sa = oa.scale;
+    a.sb = ob.scale;
     a.C = C;
     a.ldc = ldc;
     a.alpha = alpha;
@@ -539,42 +588,12 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     a.ktri = mode.ktri ? 1 : 0;
     a.tiles_m = (int)ceil_div(m, OZ_BM);
     a.tiles_n = (int)ceil_div(n, OZ_BN);
-    // Tile order.  One round of the persistent loop runs sm_count consecutive list entries concurrently and, tiles
-    // being equally long, in k-lockstep: if those tiles form a compact block of (row block, column block) pairs, each
-    // operand block is fetched from HBM once per round and served to the other tiles from L2.  Bands of G row blocks,
-    // column-major inside a band: a round covers ~G x (sm_count/G) tiles = G + sm_count/G distinct operand blocks.
     const int CL = (ctx->oz_cluster == 2) ? 2 : 1;
-    const int pairs_n = (a.tiles_n + CL - 1) / CL;   // list entries per row block: column tiles (CL = 1) or pairs of them
-    OzTileList* tl = nullptr;
-    for (auto& l : w.lists)
-        if (l.tm == a.tiles_m && l.tn == a.tiles_n && l.lower == a.lower_only && l.cl == CL) tl = &l;
-    if (!tl) {
-        // one factorisation cycles through ~2 N / panel distinct shapes; they repeat from draw to draw
-        tl = &w.lists[w.next_list];
-        w.next_list = (w.next_list + 1) % OZ_LISTS;
-        tl->host.clear();
-        const int G = 8;
-        for (int b0 = 0; b0 < a.tiles_m; b0 += G) {
-            const int b1 = b0 + G < a.tiles_m ? b0 + G : a.tiles_m;
-            // lower: row block ti owns column tiles 0 .. 2 ti + 1, i.e. pairs 0 .. ti
-            const int last = lower_only ? (CL == 2 ? b1 - 1 : 2 * (b1 - 1) + 1) : pairs_n - 1;
-            const int jmax = last < pairs_n - 1 ? last : pairs_n - 1;
-            for (int tj = 0; tj <= jmax; ++tj)
-                for (int ti = b0; ti < b1; ++ti)
-                    if (!lower_only || tj <= (CL == 2 ? ti : 2 * ti + 1)) tl->host.push_back(make_int2(ti, tj));
-        }
-        tl->tm = a.tiles_m;
-        tl->tn = a.tiles_n;
-        tl->lower = a.lower_only;
-        tl->cl = CL;
-        tl->count = (int64_t)tl->host.size();
-        // a list may still be in use by a kernel queued earlier on this stream: the copy is stream-ordered behind it
-        RET_IF(ensure(ctx, tl->dev, tl->host.size() * sizeof(int2)));
-        CUDA_TRY(ctx, cudaMemcpyAsync(tl->dev.p, tl->host.data(), tl->host.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-    }
-    const int64_t tiles = tl->count;
+    if (!list) RET_IF(oz_default_list(ctx, st, w, a.tiles_m, a.tiles_n, lower_only, CL, &list, &count));
+    if (count <= 0) return B2GP_OK;
+    const int64_t tiles = count;
     a.num_tiles = (int)tiles;
-    a.tile_list = (const int2*)tl->dev.p;
+    a.tile_list = list;
     a.prof = nullptr;
     if (w.prof.p) a.prof = (long long*)w.prof.p;
     a.debug = ctx->oz_debug;
@@ -608,6 +627,21 @@ static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, i
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
     return B2GP_OK;
+}
+
+template <int S>
+static int ozaki_gemm_nt(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                         int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, bool lower_only, OzMode mode = OzMode()) {
+    if (m <= 0 || n <= 0 || k <= 0) return B2GP_OK;
+    if (k > OZ_K_MAX) return B2GP_ERR_UNSUPPORTED;  // int32 accumulation bound (the dispatcher splits longer k)
+    const bool same = (A == B && lda == ldb && n <= m && !mode.transB);   // B's rows are the first n rows of A: one set of planes
+    OzOperand oa, ob;
+    RET_IF(oz_slice_launch<S>(ctx, st, A, lda, m, k, w.planesA, w.scaleA, false, nullptr, &oa));
+    if (same)
+        ob = oa;
+    else
+        RET_IF(oz_slice_launch<S>(ctx, st, B, ldb, n, k, w.planesB, w.scaleB, mode.transB, nullptr, &ob));
+    return oz_mma_launch<S>(ctx, st, w, oa, ob, m, n, k, alpha, C, ldc, lower_only, mode, nullptr, 0);
 }
 
 static int ozaki_dispatch(b2gp_ctx* ctx, cudaStream_t st, int64_t m, int64_t n, int64_t k, double alpha, const double* A, int64_t lda,
