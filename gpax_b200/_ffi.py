@@ -73,6 +73,14 @@ SIGNATURES = {
     "b2gp_mll": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, C.c_uint, _dp, _vp, _vp, _ip]),
     "b2gp_sparse_elbo": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, C.c_uint, _dp, _vp,
                                    _vp, _ip]),
+    "b2gp_dist_unique_id": (C.c_int, [_vp]),
+    "b2gp_dist_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "b2gp_dist_info": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
+    "b2gp_dist_finalize": (C.c_int, [_vp]),
+    "b2gp_dist_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int, C.c_double,
+                                      C.c_int64, C.c_uint, _vp, _vp, _ip, C.POINTER(Timing)]),
+    "b2gp_dist_layout": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
+                                   C.POINTER(C.c_int64)]),
     "b2gp_sparse_partial": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp,
                                       C.c_int64, _vp, _ip]),
     "b2gp_sparse_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int,

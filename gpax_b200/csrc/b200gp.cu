@@ -15,6 +15,7 @@
 #include "potrf.cuh"
 #include "sparse_elbo.cuh"
 #include "acq.cuh"
+#include "dist.cuh"
 
 // ------------------------------------------------------------------------------------------ helpers
 namespace {
@@ -60,6 +61,7 @@ struct Extra {  // ctx-private state that is not part of the struct the kernels'
         int info = 0;
     } fcache;
     int64_t cache_hits = 0;
+    DistState* dist = nullptr;   // multi-GPU state (dist.cuh), created by b2gp_dist_init
 };
 
 }  // namespace
@@ -1716,5 +1718,411 @@ extern "C" int b2gp_debug_i8_peak(b2gp_ctx* ctx, int iters, int reps, double* to
     }
     *tops_out = 2.0 * 128 * 256 * 32 * (double)iters * ctx->sm_count / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
+    return B2GP_OK;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU (dist.cuh)
+extern "C" int b2gp_dist_unique_id(void* id128) {
+    if (!id128) return B2GP_ERR_ARG;
+    NcclApi* n = nccl_api();
+    if (!n->handle || !n->error.empty()) return B2GP_ERR_UNSUPPORTED;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    if (n->GetUniqueId(&id) != ncclSuccess) return B2GP_ERR_CUDA;
+    memcpy(id128, &id, 128);
+    return B2GP_OK;
+}
+
+static int dist_free(b2gp_ctx* ctx, DistState* ds) {
+    NcclApi* n = nccl_api();
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&ds->Aloc, &ds->PB[0], &ds->PB[1], &ds->UB, &ds->Xrows, &ds->Zcols, &ds->yloc, &ds->red, &ds->linv, &ds->updA, &ds->updB,
+                      &ds->updSA, &ds->updSB, &ds->wseg})
+        free_buf(*b);
+    for (auto& st : ds->steps) {
+        free_buf(st.g1);
+        free_buf(st.g2);
+        free_buf(st.bmap);
+    }
+    for (cudaEvent_t e : {ds->ev_u, ds->ev_ubc, ds->ev_chunk, ds->ev_comm[0], ds->ev_comm[1], ds->ev_done})
+        if (e) cudaEventDestroy(e);
+    if (ds->ms) cudaStreamDestroy(ds->ms);
+    if (n->handle) {
+        if (ds->rowc) n->CommDestroy(ds->rowc);
+        if (ds->colc) n->CommDestroy(ds->colc);
+        if (ds->world) n->CommDestroy(ds->world);
+    }
+    delete ds;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_dist_finalize(b2gp_ctx* ctx) {
+    if (!ctx) return B2GP_ERR_ARG;
+    Extra* ex = extra_of(ctx);
+    if (ex->dist) {
+        dist_free(ctx, ex->dist);
+        ex->dist = nullptr;
+    }
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_dist_init(b2gp_ctx* ctx, const void* id128, int rank, int nranks, int grid_rows, int grid_cols) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, id128 && nranks >= 1 && rank >= 0 && rank < nranks);
+    ARG_CHECK(ctx, grid_rows >= 1 && grid_cols >= 1 && grid_rows * grid_cols == nranks);
+    NcclApi* n = nccl_api();
+    if (!n->handle || !n->error.empty())
+        return set_err(ctx, B2GP_ERR_UNSUPPORTED, "b2gp_dist_init", n->error.c_str(), __FILE__, __LINE__);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    if (ex->dist) RET_IF(b2gp_dist_finalize(ctx));
+    DistState* ds = new DistState();
+    ex->dist = ds;
+    ds->rank = rank;
+    ds->nranks = nranks;
+    ds->g.pr = grid_rows;
+    ds->g.pc = grid_cols;
+    ds->g.myrow = rank / grid_cols;     // row-major process grid
+    ds->g.mycol = rank % grid_cols;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(ctx, n->CommInitRank(&ds->world, nranks, id, rank));
+    // row communicator: the pc processes of my grid row, ranked by column; column communicator: the pr processes of my
+    // grid column, ranked by row
+    NCCL_TRY(ctx, n->CommSplit(ds->world, ds->g.myrow, ds->g.mycol, &ds->rowc, nullptr));
+    NCCL_TRY(ctx, n->CommSplit(ds->world, ds->g.mycol, ds->g.myrow, &ds->colc, nullptr));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ds->ms, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ds->ev_u, &ds->ev_ubc, &ds->ev_chunk, &ds->ev_comm[0], &ds->ev_comm[1], &ds->ev_done})
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    ds->ready = true;
+    return B2GP_OK;
+}
+
+extern "C" int b2gp_dist_info(b2gp_ctx* ctx, int* rank, int* nranks, int* grid_rows, int* grid_cols) {
+    if (!ctx) return B2GP_ERR_ARG;
+    DistState* ds = extra_of(ctx)->dist;
+    if (!ds || !ds->ready) return set_err(ctx, B2GP_ERR_ARG, "b2gp_dist_info", "call b2gp_dist_init first", __FILE__, __LINE__);
+    if (rank) *rank = ds->rank;
+    if (nranks) *nranks = ds->nranks;
+    if (grid_rows) *grid_rows = ds->g.pr;
+    if (grid_cols) *grid_cols = ds->g.pc;
+    return B2GP_OK;
+}
+
+// Pure index algebra of the block-cyclic layout (no GPU, no NCCL): for the process at (row, col) of a pr x pc grid,
+// out[0] = local tile rows, out[1] = local tile columns, out[2] = rows of the panel of step k it holds, out[3] = slot
+// rows of the panel buffer at step k, out[4] = first local tile row after k, out[5] = first local tile column after k.
+extern "C" int b2gp_dist_layout(int64_t T, int64_t R, int64_t nb, int pr, int pc, int row, int col, int64_t k, int64_t* out) {
+    if (!out || T < 1 || R < 0 || nb < 1 || pr < 1 || pc < 1 || row < 0 || row >= pr || col < 0 || col >= pc || k < 0) return B2GP_ERR_ARG;
+    BcGrid g;
+    g.pr = pr;
+    g.pc = pc;
+    g.myrow = row;
+    g.mycol = col;
+    g.nb = nb;
+    g.T = T;
+    g.R = R;
+    out[0] = g.lr(row);
+    out[1] = g.lc(col);
+    out[2] = g.panel_rows(k, row);
+    out[3] = g.slot_rows(k);
+    out[4] = g.first_row_after(k, row);
+    out[5] = g.first_col_after(k, col);
+    return B2GP_OK;
+}
+
+// staircase tile lists and B-operand row maps of every step, for the current grid / problem shape
+static int dist_build_steps(b2gp_ctx* ctx, DistState* ds, cudaStream_t st, int CL) {
+    const BcGrid& g = ds->g;
+    if (ds->cache_T == g.T && ds->cache_R == g.R && ds->cache_nb == g.nb && ds->cache_cl == CL) return B2GP_OK;
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));   // lists of a previous shape may still be in use
+    for (auto& s : ds->steps) {
+        free_buf(s.g1);
+        free_buf(s.g2);
+        free_buf(s.bmap);
+    }
+    ds->steps.assign((size_t)g.T, DistStep());
+    const int64_t nb = g.nb, t128 = nb / 128;          // 128-row groups per tile
+    const int64_t colw = CL == 2 ? 128 : 64;           // columns covered by one list entry
+    const int64_t ent_per_tile = nb / colw;
+    for (int64_t k = 0; k < g.T; ++k) {
+        DistStep& s = ds->steps[(size_t)k];
+        const int64_t li0 = g.first_row_after(k, g.myrow), lj0 = g.first_col_after(k, g.mycol);
+        const int64_t ntr = g.lr(g.myrow) - li0, ntc = g.lc(g.mycol) - lj0;    // local tile rows / columns of the trailing matrix
+        if (ntr <= 0 || ntc <= 0) continue;
+        // B operand: the panel tiles (gj, k) of my tile columns gj > k, found in slot gj % pr of the panel buffer
+        const int64_t slot = g.slot_rows(k);
+        std::vector<int64_t> bmap((size_t)(ntc * t128));
+        for (int64_t c = 0; c < ntc; ++c) {
+            const int64_t gj = (lj0 + c) * g.pc + g.mycol;
+            const int r = (int)(gj % g.pr);
+            const int64_t src = (int64_t)r * slot + (gj / g.pr - g.first_row_after(k, r)) * nb;
+            for (int64_t q = 0; q < t128; ++q) bmap[(size_t)(c * t128 + q)] = src + q * 128;
+        }
+        RET_IF(ensure(ctx, s.bmap, bmap.size() * 8));
+        CUDA_TRY(ctx, cudaMemcpyAsync(s.bmap.p, bmap.data(), bmap.size() * 8, cudaMemcpyHostToDevice, st));
+        // staircase: 128-row tile ti of local tile row a (global gi) x column entry of local tile column c (global gj), gi >= gj
+        std::vector<int2> l1, l2;
+        const int64_t next_col = (k + 1 < g.T && (k + 1) % g.pc == g.mycol) ? (k + 1) / g.pc - lj0 : -1;   // local index (in the trailing matrix) of tile column k+1
+        const int G = 8;
+        const int64_t rows128 = ntr * t128;
+        for (int64_t b0 = 0; b0 < rows128; b0 += G) {
+            const int64_t b1 = std::min(b0 + G, rows128);
+            for (int64_t c = 0; c < ntc; ++c) {
+                const int64_t gj = (lj0 + c) * g.pc + g.mycol;
+                for (int64_t e = 0; e < ent_per_tile; ++e)
+                    for (int64_t ti = b0; ti < b1; ++ti) {
+                        const int64_t gi = (li0 + ti / t128) * g.pr + g.myrow;
+                        if (gi < gj) continue;
+                        (c == next_col ? l1 : l2).push_back(make_int2((int)ti, (int)(c * ent_per_tile + e)));
+                    }
+            }
+        }
+        s.n1 = (int64_t)l1.size();
+        s.n2 = (int64_t)l2.size();
+        if (s.n1) {
+            RET_IF(ensure(ctx, s.g1, l1.size() * sizeof(int2)));
+            CUDA_TRY(ctx, cudaMemcpyAsync(s.g1.p, l1.data(), l1.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        }
+        if (s.n2) {
+            RET_IF(ensure(ctx, s.g2, l2.size() * sizeof(int2)));
+            CUDA_TRY(ctx, cudaMemcpyAsync(s.g2.p, l2.data(), l2.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        }
+        CUDA_TRY(ctx, cudaStreamSynchronize(st));   // the host vectors die here
+    }
+    ds->cache_T = g.T;
+    ds->cache_R = g.R;
+    ds->cache_nb = g.nb;
+    ds->cache_cl = CL;
+    return B2GP_OK;
+}
+
+// Exact-GP posterior (mean + diagonal variance) with k_XX distributed over the process grid.  COLLECTIVE: every rank
+// calls it with the same (replicated) inputs -- X, y, X_new and theta are a few hundred KB, only K is big.  HOST pointers.
+extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t N, const double* yres, const double* Xnew,
+                                   int64_t P, int d, const double* theta, int noiseless, double jitter, int64_t nb, unsigned flags,
+                                   double* mean, double* var, int* info, b2gp_timing* timing) {
+    if (!ctx) return B2GP_ERR_ARG;
+    Extra* ex = extra_of(ctx);
+    DistState* ds = ex->dist;
+    if (!ds || !ds->ready) return set_err(ctx, B2GP_ERR_ARG, "b2gp_dist_posterior", "call b2gp_dist_init first", __FILE__, __LINE__);
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xtr && yres && Xnew && theta && mean && info);
+    ARG_CHECK(ctx, N >= 1 && P >= 1 && d >= 1 && d <= GRAM_MAX_D);
+    ARG_CHECK(ctx, nb >= 128 && nb % 128 == 0 && N % nb == 0);
+    ARG_CHECK(ctx, !(flags & B2GP_FLAG_DEVICE_PTRS) && !(flags & (B2GP_OUT_COV | B2GP_OUT_SAMPLE)));
+    if (ctx->ozaki == 0) return set_err(ctx, B2GP_ERR_UNSUPPORTED, "b2gp_dist_posterior", "needs the int8 path (ozaki != 0)", __FILE__, __LINE__);
+    const bool want_var = flags & B2GP_OUT_VAR;
+    ARG_CHECK(ctx, !want_var || var);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    NcclApi* nc = nccl_api();
+    ex->fcache.valid = false;
+    Slot& sl = ctx->slots[0];
+    cudaStream_t cs = sl.stream, ms = ds->ms;
+    BcGrid& g = ds->g;
+    g.nb = nb;
+    g.T = N / nb;
+    g.R = ceil_div(P + 1, nb);
+    const int pr = g.pr, pc = g.pc, myrow = g.myrow, mycol = g.mycol;
+    const int64_t T = g.T, Lr = g.lr(myrow), Lc = g.lc(mycol), ld = Lc * nb;
+    const int CL = (ctx->oz_cluster == 2) ? 2 : 1;
+    const int nth = d + 3;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(cs));
+    RET_IF(dist_build_steps(ctx, ds, cs, CL));
+
+    // ---- inputs: the rows / columns of X this process's tiles need, gathered on the host (a few hundred KB)
+    std::vector<double> xr((size_t)(Lr * nb * d)), zc((size_t)std::max<int64_t>(Lc * nb * d, 1)), yl((size_t)std::max<int64_t>(Lc * nb, 1));
+    for (int64_t li = 0; li < Lr; ++li) {
+        const int64_t gi = li * pr + myrow;
+        for (int64_t r = 0; r < nb; ++r) {
+            const double* src;
+            if (gi < T)
+                src = Xtr + (gi * nb + r) * d;
+            else {
+                const int64_t p = (gi - T) * nb + r;
+                src = Xnew + (p < P ? p : 0) * d;       // padding rows repeat a valid point; their results are never read
+            }
+            memcpy(&xr[(size_t)((li * nb + r) * d)], src, (size_t)d * 8);
+        }
+    }
+    for (int64_t lj = 0; lj < Lc; ++lj) {
+        const int64_t gj = lj * pc + mycol;
+        memcpy(&zc[(size_t)(lj * nb * d)], Xtr + gj * nb * d, (size_t)(nb * d) * 8);
+        memcpy(&yl[(size_t)(lj * nb)], yres + gj * nb, (size_t)nb * 8);
+    }
+    RET_IF(ensure(ctx, ds->Xrows, xr.size() * 8));
+    RET_IF(ensure(ctx, ds->Zcols, zc.size() * 8));
+    RET_IF(ensure(ctx, ds->yloc, yl.size() * 8));
+    RET_IF(ensure(ctx, ctx->d_in[3], (size_t)nth * 8));
+    RET_IF(ensure(ctx, ds->Aloc, (size_t)std::max<int64_t>(Lr * nb * ld, 1) * 8));
+    RET_IF(ensure(ctx, ds->UB, (size_t)nb * nb * 8));
+    RET_IF(ensure(ctx, ds->linv, (size_t)linv_bytes(nb)));
+    RET_IF(ensure(ctx, ds->red, (size_t)(4 * P + 64) * 8));
+    RET_IF(ensure(ctx, ds->wseg, (size_t)std::max<int64_t>(ld, 1) * 8));
+    const int64_t slot0 = g.slot_rows(0);
+    for (int b = 0; b < 2; ++b) RET_IF(ensure(ctx, ds->PB[b], (size_t)std::max<int64_t>(pr * slot0 * nb, 1) * 8));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds->Xrows.p, xr.data(), xr.size() * 8, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds->Zcols.p, zc.data(), zc.size() * 8, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ds->yloc.p, yl.data(), yl.size() * 8, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_in[3].p, theta, (size_t)nth * 8, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, cs));
+    CUDA_TRY(ctx, cudaStreamSynchronize(cs));   // the host staging vectors are pageable
+    const double* dth = (const double*)ctx->d_in[3].p;
+    double* A = (double*)ds->Aloc.p;
+    double* UB = (double*)ds->UB.p;
+    sl.oz_planes = ctx->ozaki > 0 ? ctx->ozaki : oz_auto_planes((double)N, theta[d], theta[d + 1], jitter);
+
+    // ---- the local matrix, generated in place: k(rows, columns) for every local tile, then the diagonal term and y
+    if (Lr > 0 && Lc > 0) {
+        RET_IF(launch_gram(ctx, cs, kind, (const double*)ds->Xrows.p, Lr * nb, (const double*)ds->Zcols.p, Lc * nb, d, dth, 0.0, 0.0, 0, 0, A, ld));
+        int64_t gi0 = -1, step = 0, count = 0;
+        for (int64_t gi = 0; gi < T; ++gi)
+            if (gi % pr == myrow && gi % pc == mycol) {
+                if (gi0 < 0)
+                    gi0 = gi;
+                else if (step == 0)
+                    step = gi - gi0;
+                ++count;
+            }
+        if (count > 0) {
+            dist_diag_kernel<<<grid_for(count * nb), 256, 0, cs>>>(A, ld, nb, pr, pc, gi0, step ? step : 1, count, dth, d, jitter);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+        const int64_t gy = T + P / nb;                      // tile row holding the y^T right-hand side (global rhs row P)
+        if (gy % pr == myrow)
+            CUDA_TRY(ctx, cudaMemcpyAsync(A + ((gy / pr) * nb + P % nb) * ld, ds->yloc.p, (size_t)ld * 8, cudaMemcpyDeviceToDevice, cs));
+    }
+    cudaEvent_t ev_f0 = ctx->slots[0].ev[2], ev_f1 = ctx->slots[0].ev[3];
+    CUDA_TRY(ctx, cudaEventRecord(ev_f0, cs));
+
+    // ---- panel pipeline pieces
+    auto panel_front = [&](int64_t k) -> int {   // (a) .. (f) of step k; compute parts on cs, collectives on ms
+        const int kr = (int)(k % pr), kc = (int)(k % pc);
+        const int64_t li0 = g.first_row_after(k, myrow), rows = g.panel_rows(k, myrow), slot = g.slot_rows(k);
+        double* PBk = (double*)ds->PB[k & 1].p;
+        if (mycol == kc) {
+            if (myrow == kr) {
+                double* D = A + ((k / pr) * nb) * ld + (k / pc) * nb;
+                RET_IF(potrf_rec(ctx, cs, D, ld, nb, (double*)ds->linv.p, dinfo, k * nb));
+                set_identity_kernel<<<grid_for(nb * nb), 256, 0, cs>>>(UB, nb, nb);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches++;
+                RET_IF(trsm_rec(ctx, cs, UB, nb, nb, D, ld, nb, (const double*)ds->linv.p));      // U = L_kk^{-T}
+            }
+            if (pr > 1) {
+                CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, cs));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_u, 0));
+                NCCL_TRY(ctx, nc->Broadcast(UB, UB, (size_t)(nb * nb), ncclDouble, kr, ds->colc, ms));
+                CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc, ms));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
+            }
+            if (rows > 0) {
+                double* rp = A + (li0 * nb) * ld + (k / pc) * nb;
+                RET_IF(ozaki_dispatch(ctx, cs, rows, nb, nb, 1.0, rp, ld, UB, nb, rp, ld, false, true, true, true));
+                copy2d_kernel<<<grid_for(rows * nb), 256, 0, cs>>>(PBk + (int64_t)myrow * slot * nb, nb, rp, ld, rows, nb);
+                CUDA_TRY(ctx, cudaGetLastError());
+                ctx->launches++;
+            }
+        }
+        if (slot > 0) {
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_chunk, cs));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_chunk, 0));
+            double* mine = PBk + (int64_t)myrow * slot * nb;
+            if (pc > 1) NCCL_TRY(ctx, nc->Broadcast(mine, mine, (size_t)(slot * nb), ncclDouble, kc, ds->rowc, ms));
+            if (pr > 1) NCCL_TRY(ctx, nc->AllGather(mine, PBk, (size_t)(slot * nb), ncclDouble, ds->colc, ms));
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ds->ev_comm[k & 1], ms));
+        return B2GP_OK;
+    };
+    OzOperand opA, opB;
+    OzMode upd_mode;
+    auto update_slices = [&](int64_t k) -> int {   // digit planes of the panel of step k for this process's rows and columns
+        const DistStep& s = ds->steps[(size_t)k];
+        const int64_t rows = g.panel_rows(k, myrow), cols = (Lc - g.first_col_after(k, mycol)) * nb, slot = g.slot_rows(k);
+        if (rows <= 0 || cols <= 0 || s.n1 + s.n2 == 0) return B2GP_OK;
+        const double* PBk = (const double*)ds->PB[k & 1].p;
+        if (sl.oz_planes == 6) {
+            RET_IF(oz_slice_launch<6>(ctx, cs, PBk + (int64_t)myrow * slot * nb, nb, rows, nb, ds->updA, ds->updSA, false, nullptr, &opA));
+            RET_IF(oz_slice_launch<6>(ctx, cs, PBk, nb, cols, nb, ds->updB, ds->updSB, false, (const int64_t*)s.bmap.p, &opB));
+        } else {
+            RET_IF(oz_slice_launch<7>(ctx, cs, PBk + (int64_t)myrow * slot * nb, nb, rows, nb, ds->updA, ds->updSA, false, nullptr, &opA));
+            RET_IF(oz_slice_launch<7>(ctx, cs, PBk, nb, cols, nb, ds->updB, ds->updSB, false, (const int64_t*)s.bmap.p, &opB));
+        }
+        return B2GP_OK;
+    };
+    auto update_part = [&](int64_t k, int part) -> int {   // (g1) / (g2) of step k
+        const DistStep& s = ds->steps[(size_t)k];
+        const int64_t cnt = part == 1 ? s.n1 : s.n2;
+        if (cnt == 0) return B2GP_OK;
+        const int64_t li0 = g.first_row_after(k, myrow), lj0 = g.first_col_after(k, mycol);
+        const int64_t rows = g.panel_rows(k, myrow), cols = (Lc - lj0) * nb;
+        double* C = A + (li0 * nb) * ld + lj0 * nb;
+        const int2* list = (const int2*)(part == 1 ? s.g1.p : s.g2.p);
+        if (sl.oz_planes == 6) return oz_mma_launch<6>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt);
+        return oz_mma_launch<7>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt);
+    };
+
+    // ---- the factorisation (with the right-hand-side rows riding below)
+    RET_IF(panel_front(0));
+    for (int64_t k = 0; k < T; ++k) {
+        CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_comm[k & 1], 0));
+        RET_IF(update_slices(k));
+        RET_IF(update_part(k, 1));
+        if (k + 1 < T) RET_IF(panel_front(k + 1));
+        RET_IF(update_part(k, 2));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(ev_f1, cs));
+
+    // ---- epilogue: mean[p] = <V[p, :], w>, var[p] = k(x,x) + noise_p + jitter - |V[p, :]|^2, summed over the process grid
+    double* red = (double*)ds->red.p;        // [0, P): dot, [P, 2P): |V|^2
+    CUDA_TRY(ctx, cudaMemsetAsync(red, 0, (size_t)(2 * P) * 8, cs));
+    {
+        const int64_t gy = T + P / nb;
+        double* wseg = (double*)ds->wseg.p;
+        if (gy % pr == myrow && Lc > 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(wseg, A + ((gy / pr) * nb + P % nb) * ld, (size_t)ld * 8, cudaMemcpyDeviceToDevice, cs));
+        if (pr > 1 && Lc > 0) {
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, cs));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_u, 0));
+            NCCL_TRY(ctx, nc->Broadcast(wseg, wseg, (size_t)ld, ncclDouble, (int)(gy % pr), ds->colc, ms));
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc, ms));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
+        }
+        for (int64_t li = 0; li < Lr && Lc > 0; ++li) {
+            const int64_t gi = li * pr + myrow;
+            if (gi < T) continue;
+            const int64_t p0 = (gi - T) * nb, np = std::min<int64_t>(nb, P - p0);
+            if (np <= 0) continue;
+            rowdot2_kernel<<<(unsigned)np, RD_THREADS, 0, cs>>>(A + (li * nb) * ld, ld, ld, wseg, 1.0, red + p0, red + P + p0);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+        }
+        CUDA_TRY(ctx, cudaEventRecord(ds->ev_chunk, cs));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_chunk, 0));
+        NCCL_TRY(ctx, nc->AllReduce(red, red, (size_t)(2 * P), ncclDouble, ncclSum, ds->world, ms));
+        NCCL_TRY(ctx, nc->AllReduce(dinfo, dinfo, 1, ncclInt, ncclMax, ds->world, ms));
+        CUDA_TRY(ctx, cudaEventRecord(ds->ev_done, ms));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_done, 0));
+        dist_finish_kernel<<<grid_for(P), 256, 0, cs>>>(red, want_var ? red + 2 * P : nullptr, red + P, P, kind, d, dth, noiseless ? 0.0 : 1.0,
+                                                         jitter, dinfo);
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->launches++;
+    }
+    CUDA_TRY(ctx, cudaMemcpyAsync(mean, red, (size_t)P * 8, cudaMemcpyDeviceToHost, cs));
+    if (want_var) CUDA_TRY(ctx, cudaMemcpyAsync(var, red + 2 * P, (size_t)P * 8, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(ctx, cudaMemcpyAsync(info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, cs));
+    RET_IF(tm.end(cs, nullptr));
+    sl.oz_planes = 7;
+    float ms_f = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms_f, ev_f0, ev_f1));
+    ex->last.potrf_ms = ms_f;
+    const double n = (double)N, p = (double)P;
+    ex->last.flops = n * n * n / 3.0 + n * n * (p + 1.0) + 4.0 * n * p;
+    if (timing) *timing = ex->last;
     return B2GP_OK;
 }

@@ -235,6 +235,26 @@ int  b2gp_kg(b2gp_ctx* ctx, const double* mean, const double* cov, int64_t P, co
  * (panel broadcast, M x M all-reduce) are issued by the host side over NCCL on these same device
  * buffers (gpax_b200/distributed.py).  All array pointers below are DEVICE pointers. ----------------*/
 
+/* ---- in-library multi-GPU (one process per GPU, NCCL loaded at run time; gpax_b200/csrc/dist.cuh) ------------------
+ * b2gp_dist_unique_id: rank 0 obtains the 128-byte NCCL id and hands it to the other ranks by any host channel
+ *   (gpax_b200/dist.py uses a TCP socket at MASTER_ADDR).  b2gp_dist_init: every rank, same id; builds the world
+ *   communicator and the row / column communicators of a grid_rows x grid_cols process grid (rank = row * grid_cols + col).
+ * b2gp_dist_posterior (COLLECTIVE, host pointers, inputs replicated on every rank): exact-GP posterior mean and diagonal
+ *   variance -- gpax/models/gp.py:253-277 / gpax/models/vigp.py:178-185 -- with k_XX 2-D block-cyclic over the grid in
+ *   nb x nb tiles (N a multiple of nb, nb a multiple of 128), generated in place; right-looking Cholesky with the panel
+ *   solve spread over the process column, the panel broadcast along process rows and all-gathered down process columns,
+ *   look-ahead of one panel, trailing updates on the int8 tcgen05 kernel; the right-hand sides ride below the matrix.
+ *   Every rank receives mean[P], var[P] (B2GP_OUT_VAR) and info.
+ * b2gp_dist_layout: the block-cyclic index algebra as a pure function (no GPU), see dist.cuh.                         */
+int  b2gp_dist_unique_id(void* id128);
+int  b2gp_dist_init(b2gp_ctx* ctx, const void* id128, int rank, int nranks, int grid_rows, int grid_cols);
+int  b2gp_dist_info(b2gp_ctx* ctx, int* rank, int* nranks, int* grid_rows, int* grid_cols);
+int  b2gp_dist_finalize(b2gp_ctx* ctx);
+int  b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t N, const double* yres,
+                         const double* Xnew, int64_t P, int d, const double* theta, int noiseless, double jitter,
+                         int64_t nb, unsigned flags, double* mean, double* var, int* info, b2gp_timing* timing);
+int  b2gp_dist_layout(int64_t T, int64_t R, int64_t nb, int pr, int pc, int row, int col, int64_t k, int64_t* out6);
+
 /* N-sharded sparse posterior: per-shard statistics, then the posterior from their sum.
  *   Kpart[M,M] (lower) = W W^T / noise,  cpart[M] = W y / noise  with W = Luu^{-1} K(Xu, Xtr_shard)
  *   (gpax/models/sparse_gp.py:193-199, 203-204 restricted to a shard; sums over shards give the full terms).
