@@ -24,6 +24,7 @@ def main():
     kernel, out = sys.argv[6], sys.argv[7]
     from gpax_b200 import dist
     dc = dist.DistContext(grid=(pr, pc))
+    dc.ctx.set_option("ozaki", int(os.environ.get("B200GP_TEST_OZAKI", "-1")))
     X, y, Xn, theta = problem(N, P, kernel)
     res = dc.posterior(kernel, X, y, Xn, theta, nb=nb)
     res2 = dc.posterior(kernel, X, y, Xn, theta, nb=nb)          # a second call reuses the cached lists / buffers
