@@ -234,6 +234,77 @@ def cpu_baseline(budget_s=30.0):
             "best_cpu_formulation": {"value": best["value"], "unit": "posteriors/s", "sample": best["sample"]}}
 
 
+def dist_workloads(ctx, ffi, rank, world, local, td, steps=3):
+    """The two BASELINE configs whose data path has a real exchange step, run inside libb200gp.so over
+    NCCL (gpax_b200/csrc/dist.cuh) -- STRONG scaling, reported as extra objects of the bench line:
+      c4  ExactGP RBF N=32768 d=3 P=1024: k_XX 2-D block-cyclic over the process grid (2 x 4 on 8 GPUs), panel broadcast /
+          all-gather on row / column communicators, one posterior (mean + diag variance) per step
+      c5  viSparseGP Matern N=262144 d=2, M=4096 inducing points, P=4096: N-sharded statistics + one M x M all-reduce
+    With one GPU the same problems run through the single-GPU entry points (the strong-scaling baseline)."""
+    from gpax_b200 import dist
+    out = {}
+    # ---- c4
+    N, d, P, nb = 32768, 3, 1024, 512
+    rng = np.random.default_rng(5)
+    X = rng.uniform(0, 1, (N, d))
+    y = np.sin(3 * X[:, 0]) * np.cos(2 * X[:, 1]) + X[:, 2] + 0.1 * rng.standard_normal(N)
+    Xn = rng.uniform(0, 1, (P, d))
+    theta = np.array([0.3, 0.3, 0.3, 1.0, 0.1, 1.0])
+    dc = None
+    if world > 1:
+        dc = dist.DistContext(ctx=ctx, rank=rank, world=world)
+
+    def timed(fn):
+        fn()                                   # warm-up: allocations, tile lists, NCCL channels
+        ms, fac = [], []
+        for _ in range(steps):
+            barrier_sync(td, local)
+            r = fn()
+            t = ctx.last_timing()
+            ms.append(t["total_ms"])
+            fac.append(t["potrf_ms"])
+        return r, max_over_ranks(td, local, float(np.mean(ms))), max_over_ranks(td, local, float(np.mean(fac)))
+
+    if world > 1:
+        r, ms, fac = timed(lambda: dc.posterior("RBF", X, y, Xn, theta, nb=nb))
+        grid = f"{dc.grid[0]}x{dc.grid[1]}"
+    else:
+        r, ms, fac = timed(lambda: ctx.posterior("RBF", X, y, Xn, theta[None], want=("mean", "var")))
+        r = {"mean": r["mean"][0], "var": r["var"][0], "info": int(r["info"][0])}
+        grid = "1x1 (single-GPU entry point)"
+    assert r["info"] == 0 and np.isfinite(r["mean"]).all() and (r["var"] > 0).all()
+    flops = N ** 3 / 3 + N * N * (P + 1)
+    out["c4_blockcyclic"] = {"workload": "exactgp_rbf_N32768_d3_P1024", "scaling": "strong", "n_gpus": world, "grid": grid, "tile": nb,
+                             "ms_per_posterior": ms, "posteriors_per_s": 1e3 / ms, "factorisation_ms": fac if world > 1 else None,
+                             "fp64_equiv_tflops_aggregate": flops / ms / 1e9, "checksum_mean": float(np.abs(r["mean"]).sum()),
+                             "collectives": "column-comm broadcast of L_kk^-T, row-comm broadcast + column-comm all-gather of the panel "
+                                            "(NCCL inside libb200gp.so), final all-reduce of mean / var" if world > 1 else "none"}
+    # ---- c5
+    N, d, M, P = 262144, 2, 4096, 4096
+    rng = np.random.default_rng(6)
+    X = rng.uniform(0, 1, (N, d))
+    y = np.sin(9 * X[:, 0]) * np.cos(7 * X[:, 1]) + 0.05 * rng.standard_normal(N)
+    Xu = X[rng.choice(N, M, replace=False)]
+    Xn = rng.uniform(0, 1, (P, d))
+    theta = np.array([0.2, 0.2, 1.0, 0.05, 1.0])
+    if world > 1:
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        r, ms, _ = timed(lambda: dc.sparse_posterior("Matern", Xu, X[lo:hi], y[lo:hi], Xn, theta, jitter=1e-5))
+        allred = max_over_ranks(td, local, ctx.last_timing()["trsm_ms"])
+    else:
+        r, ms, _ = timed(lambda: ctx.sparse_posterior("Matern", Xu, X, y, Xn, theta, jitter=1e-5, want=("mean", "var")))
+        allred = None
+    assert r["info"] == 0 and np.isfinite(r["mean"]).all()
+    flops = 2.0 * M * M * N + 2.0 * M ** 3 / 3 + 2.0 * M * M * (P + 1)
+    out["c5_sharded_sparse"] = {"workload": "visparsegp_matern_N262144_d2_M4096_P4096", "scaling": "strong", "n_gpus": world,
+                                "ms_per_posterior": ms, "posteriors_per_s": 1e3 / ms, "allreduce_ms": allred,
+                                "fp64_equiv_tflops_aggregate": flops / ms / 1e9, "checksum_mean": float(np.abs(r["mean"]).sum()),
+                                "collectives": "one all-reduce of the M x M statistics (134 MB) inside libb200gp.so" if world > 1 else "none"}
+    if dc is not None:
+        dc.close()
+    return out
+
+
 def run_reference_arm(args, rank, budget_s=270.0):
     """--impl reference: the reference's own CPU formulation (gpax cannot be imported: JAX absent; the oracle is
     its op-for-op NumPy restatement), all host threads, same config / metric / unit.
@@ -285,9 +356,10 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--draws", type=int, default=None, help="posterior draws per step (default 8)")
+    ap.add_argument("--no-dist", action="store_true", help="skip the c4 / c5 exchange-step workloads")
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (experiments)")
     args = ap.parse_args()
 
@@ -369,7 +441,32 @@ def main():
     h2d = X.nbytes + y.nbytes + Xn.nbytes + theta.nbytes
     d2h = hmean.nbytes + hvar.nbytes + info.nbytes
 
+    for a in (dX, dy, dXn, dth, dmean, dvar):
+        a.free()
+
+    def exchange_workloads(line):
+        """c4 / c5 (every rank takes part).  They come AFTER the headline measurement and under a watchdog: a hang in a
+        collective must not cost the bench line -- rank 0 then prints the line without these extras and the ranks exit."""
+        if args.no_dist:
+            return {}
+
+        def bail():
+            if rank == 0 and line is not None:
+                line["dist_error"] = "c4 / c5 workloads did not finish within 600 s"
+                emit(json.dumps(line))
+            os._exit(0)
+        wd = threading.Timer(600.0, bail)
+        wd.daemon = True
+        wd.start()
+        try:
+            return dist_workloads(ctx, ffi, rank, world, local, td)
+        except Exception as e:  # noqa: BLE001
+            return {"dist_error": repr(e)[:400]}
+        finally:
+            wd.cancel()
+
     if rank != 0:
+        exchange_workloads(None)
         if td is not None:
             td.destroy_process_group()
         return
@@ -381,11 +478,27 @@ def main():
     except Exception as e:  # noqa: BLE001
         peak64, peak_src = 35.5, f"fallback 35.5 TFLOP/s (cuBLAS DGEMM measured on this pool, profiles/); live measure failed: {e!r}"
     peak = peak64
+    # int8 tensor peak: MEASURED in this run by a bare tcgen05.mma kind::i8 loop (oz_i8_peak_kernel: M128 N256 K32, operands
+    # resident in shared memory, every SM) -- MEASURED_PEAKS.json has no int8 figure, and 2 x its cuBLAS bf16 number
+    # (3.46 POP/s, last round's denominator) understates the pipe, which the probe runs at 4.5 POP/s
+    int8_peak, int8_src = None, None
     try:
-        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        int8_peak, int8_src = 2.0 * float(mp["bf16_tflops"]), "2 x MEASURED_PEAKS.json bf16_tflops (int8 tcgen05 rate = 2 x bf16), of measured"
+        import ctypes as C_
+        fn = ctx.lib.b2gp_debug_i8_peak
+        fn.restype = C_.c_int
+        fn.argtypes = [C_.c_void_p, C_.c_int, C_.c_int, C_.POINTER(C_.c_double), C_.POINTER(C_.c_double)]
+        tops, pms = C_.c_double(), C_.c_double()
+        if fn(ctx.h, 32768, 3, C_.byref(tops), C_.byref(pms)) == 0:
+            int8_peak, int8_src = float(tops.value), "measured in this run: oz_i8_peak_kernel (bare tcgen05.mma kind::i8 M128 N256 K32 loop on all SMs)"
     except Exception:  # noqa: BLE001
-        int8_peak, int8_src = 2.0 * 1590.0, "2 x 1.59 PFLOP/s bf16, of fallback (B200_PROFILING.md)"
+        pass
+    mp_bf16 = None
+    try:
+        mp_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:  # noqa: BLE001
+        pass
+    if int8_peak is None:
+        int8_peak, int8_src = 2.0 * (mp_bf16 or 1590.0), "2 x bf16 tensor peak (MEASURED_PEAKS.json or the B200_PROFILING.md fallback): the int8 probe failed"
     traffic = None
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel.json")))
@@ -416,6 +529,7 @@ def main():
                      "traffic": traffic, "kernel": f"oz_slice_kernel<{dom['planes']}> + oz_mma_kernel<{dom['planes']},2> (UTCIMMA M128 N<=256 K32 over stacked digit planes, TMEM "
                      "accumulators, CTA-pair TMA multicast, 32B-swizzle stages; SYRK 8192x8192 k=8192 lower)", "int8_ops_per_launch": dom["int8_ops_per_launch"],
                      "ms_per_launch": oz["ms"], "peak_source": int8_src,
+                     "frac_of_2x_measured_bf16": (int8_tops / (2.0 * mp_bf16)) if mp_bf16 else None,
                      "fp64_equiv_tflops": oz["fp64_equiv_tflops"], "fp64_equiv_over_cublas_dgemm": oz["fp64_equiv_tflops"] / peak64,
                      "digit_planes": dom["planes"], "plane_pairs": dom["pairs"]},
         # the fp64 DMMA kernel (gemm_tma_kernel) that the int8 path replaces for large updates, same launch
@@ -423,6 +537,7 @@ def main():
                           "frac": dom["dmma"]["fp64_equiv_tflops"] / peak64, "ms_per_launch": dom["dmma"]["ms"],
                           "kernel": "gemm_tma_kernel<3,2> (DMMA.8x8x4, TMA + mbarrier) + 64x64 tail launch", "peak_source": peak_src},
     }
+    line.update(exchange_workloads(line))
     if not args.no_cpu_baseline and world == 1:      # a reported baseline of the N=1 line only
         line["cpu_baseline"] = cpu_baseline()
     emit(json.dumps(line))

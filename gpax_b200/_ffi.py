@@ -79,6 +79,8 @@ SIGNATURES = {
     "b2gp_dist_finalize": (C.c_int, [_vp]),
     "b2gp_dist_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int, C.c_double,
                                       C.c_int64, C.c_uint, _vp, _vp, _ip, C.POINTER(Timing)]),
+    "b2gp_dist_sparse_posterior": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_int,
+                                             C.c_double, C.c_uint, _vp, _vp, _ip, C.POINTER(Timing)]),
     "b2gp_dist_layout": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                    C.POINTER(C.c_int64)]),
     "b2gp_sparse_partial": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp, C.c_double, _vp,

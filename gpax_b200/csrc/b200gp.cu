@@ -924,7 +924,7 @@ static int sparse_partial_dev(b2gp_ctx* ctx, Slot& sl, int kind, const double* d
     RET_IF(potrf_rec(ctx, st, Luu, ldM, M, LinvU, dinfo, 0));                                   // sparse_gp.py:194
     // W^T = K_fu Luu^{-T}  (W = Luu^{-1} Kuf, sparse_gp.py:195-197), one training point per row
     RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wt, ldM));
-    RET_IF(trsm_rec(ctx, st, Wt, ldM, N, Luu, ldM, M, LinvU));
+    RET_IF(trsm_rec(ctx, st, Wt, ldM, N, Luu, ldM, M, LinvU));   // tall right-hand sides: int8 panel GEMMs (potrf.cuh)
     {
         dim3 g((unsigned)ceil_div(M, 32), (unsigned)ceil_div(N, 32)), b(32, 8);
         transpose_kernel<<<g, b, 0, st>>>(W, ldN, Wt, ldM, N, M);
@@ -2123,6 +2123,85 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     ex->last.potrf_ms = ms_f;
     const double n = (double)N, p = (double)P;
     ex->last.flops = n * n * n / 3.0 + n * n * (p + 1.0) + 4.0 * n * p;
+    if (timing) *timing = ex->last;
+    return B2GP_OK;
+}
+
+// N-sharded sparse (Nystrom / VFE) posterior -- gpax/models/sparse_gp.py:173-223 with the training set split over the
+// ranks (config 5).  COLLECTIVE, HOST pointers: every rank passes ITS shard (Xtr_shard[N_shard, d], y_shard) and the same
+// Xu, X_new, theta.  Per rank: Luu, W = Luu^{-1} K(Xu, shard) and the statistics W W^T / noise, W y / noise
+// (sparse_gp.py:193-199, 203-204 restricted to the shard); ONE in-library NCCL all-reduce of the M x M matrix and the
+// M-vector; then the M x M Cholesky and the P-side solves replicated on every rank (sparse_gp.py:200-217).
+extern "C" int b2gp_dist_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* Xtr_shard,
+                                          int64_t N_shard, const double* y_shard, const double* Xnew, int64_t P, int d,
+                                          const double* theta, int noiseless, double jitter, unsigned flags, double* mean,
+                                          double* var, int* info, b2gp_timing* timing) {
+    if (!ctx) return B2GP_ERR_ARG;
+    Extra* ex = extra_of(ctx);
+    DistState* ds = ex->dist;
+    if (!ds || !ds->ready) return set_err(ctx, B2GP_ERR_ARG, "b2gp_dist_sparse_posterior", "call b2gp_dist_init first", __FILE__, __LINE__);
+    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, Xu && Xtr_shard && y_shard && Xnew && theta && mean && info);
+    ARG_CHECK(ctx, M >= 1 && N_shard >= 1 && P >= 1 && d >= 1 && d <= GRAM_MAX_D);
+    ARG_CHECK(ctx, !(flags & B2GP_FLAG_DEVICE_PTRS) && !(flags & (B2GP_OUT_COV | B2GP_OUT_SAMPLE)));
+    const bool want_var = flags & B2GP_OUT_VAR;
+    ARG_CHECK(ctx, !want_var || var);
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    NcclApi* nc = nccl_api();
+    ex->fcache.valid = false;
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream, ms = ds->ms;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    const int nth = d + 3;
+    const double *dXu, *dXtr, *dy, *dXnew, *dth;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], Xtr_shard, (size_t)N_shard * d * 8, false, &dXtr));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], y_shard, (size_t)N_shard * 8, false, &dy));
+    RET_IF(stage_in(ctx, st, ctx->d_in[2], Xnew, (size_t)P * d * 8, false, &dXnew));
+    RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, false, &dth));
+    RET_IF(stage_in(ctx, st, ctx->d_in[5], Xu, (size_t)M * d * 8, false, &dXu));
+    const int64_t ldM = round_up(M, 8);
+    RET_IF(ensure(ctx, sl.A, (size_t)(2 * M * ldM + ldM) * 8));      // Luu | K (+ the M-vector right behind it: one all-reduce)
+    RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
+    RET_IF(ensure(ctx, ctx->d_out[0], (size_t)(2 * P + 16) * 8));
+    RET_IF(ensure(ctx, ctx->d_info, 64));
+    int* dinfo = (int*)ctx->d_info.p;
+    CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
+    double* Luu = (double*)sl.A.p;
+    double* Kmat = Luu + M * ldM;
+    double* cvec = Kmat + M * ldM;
+    double* LinvU = (double*)sl.Linv.p;
+    double* LinvK = LinvU + linv_bytes(M) / 8;
+    double* mv = (double*)ctx->d_out[0].p;
+    double* vv = mv + P;
+    cudaEvent_t e0 = sl.ev[2], e1 = sl.ev[3], e2 = sl.ev[4];
+    CUDA_TRY(ctx, cudaEventRecord(e0, st));
+    RET_IF(sparse_partial_dev(ctx, sl, kind, dXu, M, dXtr, N_shard, dy, d, dth, jitter, theta[d + 1], Luu, ldM, LinvU, Kmat, ldM, cvec, dinfo));
+    CUDA_TRY(ctx, cudaEventRecord(e1, st));
+    if (ds->nranks > 1) {
+        CUDA_TRY(ctx, cudaEventRecord(ds->ev_chunk, st));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_chunk, 0));
+        NCCL_TRY(ctx, nc->AllReduce(Kmat, Kmat, (size_t)(M * ldM + M), ncclDouble, ncclSum, ds->world, ms));   // sparse_gp.py:199, 204 summed over shards
+        NCCL_TRY(ctx, nc->AllReduce(dinfo, dinfo, 1, ncclInt, ncclMax, ds->world, ms));
+        CUDA_TRY(ctx, cudaEventRecord(ds->ev_done, ms));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(st, ds->ev_done, 0));
+    }
+    CUDA_TRY(ctx, cudaEventRecord(e2, st));
+    RET_IF(sparse_finish_dev(ctx, sl, kind, dXu, M, Luu, ldM, LinvU, Kmat, ldM, LinvK, cvec, dXnew, P, d, dth, noiseless, jitter, want_var,
+                             false, mv, vv, nullptr, P, dinfo));
+    int hinfo[2] = {0, 0};
+    CUDA_TRY(ctx, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(ctx, cudaMemcpyAsync(mean, mv, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    if (want_var) CUDA_TRY(ctx, cudaMemcpyAsync(var, vv, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
+    RET_IF(tm.end(st, nullptr));
+    info[0] = hinfo[0] != 0 ? hinfo[0] : -hinfo[1];
+    float f = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&f, e0, e1));
+    ex->last.potrf_ms = f;          // per-rank statistics (Gram, Luu, W, W W^T)
+    CUDA_TRY(ctx, cudaEventElapsedTime(&f, e1, e2));
+    ex->last.trsm_ms = f;           // the all-reduce
+    const double m = (double)M, n = (double)N_shard * ds->nranks, p = (double)P;
+    ex->last.flops = 2.0 * m * m * m / 3.0 + 2.0 * m * m * n + 2.0 * m * m * (p + 1.0);
     if (timing) *timing = ex->last;
     return B2GP_OK;
 }

@@ -549,9 +549,18 @@ static int launch_trsm_strip(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t 
 
 // B (m x n, one right-hand side per row) <- B L^{-T}; L is n x n lower at `L`, its inverted diagonal
 // blocks at `Linv` (block b0 first).
+static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* rows, int64_t ldr, int64_t r, const double* L,
+                                int64_t ldl, int64_t n, const double* Linv128);
+
 static int trsm_rec(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl,
                     int64_t n, const double* Linv) {
     if (m <= 0 || n <= 0) return B2GP_OK;
+    // many right-hand sides against a factor block of at most `panel` columns: the explicit inverse of the block and ONE
+    // int8 tcgen05 GEMM over all rows (see potrf_tall) instead of m/32 strips at a fraction of the DMMA rate
+    if (n > B2GP_LEAF && n <= ctx->panel && m >= 1024 && ctx->ozaki != 0) {
+        Slot* sl = slot_of(ctx, st);
+        if (sl) return panel_solve_all_rows(ctx, st, *sl, B, ldb, m, L, ldl, n, Linv);
+    }
     if (n <= B2GP_LEAF) {
         // in place: C aliases A, one column tile
         return gemm_nt(ctx, st, m, n, n, 1.0, B, ldb, Linv, 128, 0.0, B, ldb, false);

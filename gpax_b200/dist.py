@@ -116,6 +116,26 @@ class DistContext:
         return {"mean": mean, "var": var, "info": info.value, "timing": t.as_dict()}
 
 
+def _sparse_posterior(self, kind, Xu, Xtr_shard, y_shard, Xnew, theta, noiseless=False, jitter=1e-6, want_var=True):
+    """COLLECTIVE.  N-sharded sparse posterior: this rank's shard of (X, y), the same Xu / X_new / theta on every rank."""
+    Xu, Xs, Xnew = _ffi._f64(Xu), _ffi._f64(Xtr_shard), _ffi._f64(Xnew)
+    M, d = Xu.shape
+    Ns, P = Xs.shape[0], Xnew.shape[0]
+    theta = _ffi._f64(theta).reshape(d + 3)
+    ys = _ffi._f64(y_shard).reshape(Ns)
+    mean, var = np.empty(P), (np.empty(P) if want_var else None)
+    info = C.c_int(0)
+    t = _ffi.Timing()
+    flags = _ffi.OUT_MEAN | (_ffi.OUT_VAR if want_var else 0)
+    self.ctx._check(self.ctx.lib.b2gp_dist_sparse_posterior(
+        self.ctx.h, _ffi.KIND[kind] if isinstance(kind, str) else kind, _ffi._ptr(Xu), M, _ffi._ptr(Xs), Ns, _ffi._ptr(ys), _ffi._ptr(Xnew),
+        P, d, _ffi._ptr(theta), int(bool(noiseless)), float(jitter), flags, _ffi._ptr(mean), _ffi._ptr(var), C.byref(info), C.byref(t)))
+    return {"mean": mean, "var": var, "info": info.value, "timing": t.as_dict()}
+
+
+DistContext.sparse_posterior = _sparse_posterior
+
+
 def layout(T, R, nb, pr, pc, row, col, k):
     """b2gp_dist_layout: (local tile rows, local tile cols, panel rows at step k, slot rows, first row after k, first col after k)"""
     lib = _ffi.load_library()

@@ -253,6 +253,13 @@ int  b2gp_dist_finalize(b2gp_ctx* ctx);
 int  b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t N, const double* yres,
                          const double* Xnew, int64_t P, int d, const double* theta, int noiseless, double jitter,
                          int64_t nb, unsigned flags, double* mean, double* var, int* info, b2gp_timing* timing);
+/* b2gp_dist_sparse_posterior (COLLECTIVE, host pointers): N-sharded Nystrom / VFE posterior --
+ *   gpax/models/sparse_gp.py:173-223 -- every rank passes ITS shard of the training set and the same Xu, X_new, theta;
+ *   per-rank statistics, one NCCL all-reduce of the M x M matrix + M-vector inside the library, replicated finish.    */
+int  b2gp_dist_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, int64_t M, const double* Xtr_shard, int64_t N_shard,
+                                const double* y_shard, const double* Xnew, int64_t P, int d, const double* theta,
+                                int noiseless, double jitter, unsigned flags, double* mean, double* var, int* info,
+                                b2gp_timing* timing);
 int  b2gp_dist_layout(int64_t T, int64_t R, int64_t nb, int pr, int pc, int row, int col, int64_t k, int64_t* out6);
 
 /* N-sharded sparse posterior: per-shard statistics, then the posterior from their sum.

@@ -1,8 +1,9 @@
 #!/bin/bash
-# usage: tools/gpurun_retry.sh <timeout_s> '<command>'   -- retries while the pod answers "busy" (exit 3)
+# usage: [GPUS=N] tools/gpurun_retry.sh <timeout_s> '<command>'   -- retries while the pod answers "busy" (exit 3)
 T=$1; shift
+G=""; [ -n "$GPUS" ] && G="--gpus $GPUS"
 for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout "$T" -- "$@"
+  /usr/local/graft/bin/gpurun $G --timeout "$T" -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 90
