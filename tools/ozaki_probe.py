@@ -1,4 +1,4 @@
-"""ozaki_test.py -- int8-tcgen05 (Ozaki) GEMM/SYRK vs the DMMA kernel and NumPy; timing at the headline SYRK size."""
+"""ozaki_probe.py -- int8-tcgen05 (Ozaki) GEMM/SYRK vs the DMMA kernel and NumPy; timing at the headline SYRK size."""
 import ctypes as C
 import sys
 
@@ -48,19 +48,24 @@ def run(S, m, n, k, lower, same, check=True, reps=1):
 
 mode = sys.argv[1] if len(sys.argv) > 1 else "small"
 if mode == "small":
-    for S in (8, 7):
+    for S in (7, 6):
         run(S, 128, 64, 64, False, False)
         run(S, 128, 64, 256, False, False)
         run(S, 256, 192, 128, False, False)
         run(S, 300, 100, 70, False, False)
         run(S, 512, 512, 200, True, True)
         run(S, 1024, 1024, 1024, True, True)
-elif mode == "prof":
-    for kk in (512, 2048, 8192):
-        run(8, 8192, 8192, kk, True, True, check=False, reps=2)
-    run(8, 8192, 8192, 2048, False, False, check=False, reps=2)
+elif mode == "prof":          # run with B2GP_OZ_PROF=1: issuer / epilogue cycle counters per tile; cluster 2 and 1
+    for cl in (2, 1):
+        ctx.set_option("oz_cluster", cl)
+        print(f"--- oz_cluster = {cl}", flush=True)
+        for S in (6, 7):
+            for kk in (512, 1024, 8192):
+                run(S, 8192, 8192, kk, True, True, check=False, reps=2)
+            run(S, 8192, 8192, 2048, False, False, check=False, reps=2)
+    ctx.set_option("oz_cluster", 2)
 else:
-    for S in (8, 7):
+    for S in (7, 6):
         run(S, 4096, 4096, 4096, True, True, check=True, reps=2)
         run(S, 8192, 8192, 8192, True, True, check=False, reps=3)
         run(S, 8192, 8192, 8192, False, False, check=False, reps=2)
