@@ -18,6 +18,7 @@ KIND = {"RBF": KERNEL_RBF, "Matern": KERNEL_MATERN52, "Periodic": KERNEL_PERIODI
 
 FLAG_DEVICE_PTRS = 1 << 0
 FLAG_LOWER_ONLY = 1 << 1
+FLAG_F32 = 1 << 2
 OUT_MEAN, OUT_VAR, OUT_COV, OUT_SAMPLE = 1 << 4, 1 << 5, 1 << 6, 1 << 7
 
 
@@ -126,6 +127,13 @@ def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 
 
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
 def _f64(a, shape=None):
     a = np.ascontiguousarray(a, dtype=np.float64)
     if shape is not None:
@@ -227,17 +235,19 @@ class Context:
         return arr
 
     # ---- primitives (host arrays in / out)
-    def gram(self, kind, X, Z, lengthscale, scale, period=1.0, diag_add=0.0, same_xz=None, lower_only=False):
-        X, Z = _f64(X), _f64(Z)
+    def gram(self, kind, X, Z, lengthscale, scale, period=1.0, diag_add=0.0, same_xz=None, lower_only=False, f32=False):
+        """f32: X, Z are handed over as float32 and K comes back float32 (B2GP_FLAG_F32)"""
+        cv, dt = (_f32, np.float32) if f32 else (_f64, np.float64)
+        X, Z = cv(X), cv(Z)
         n, d = X.shape
         m = Z.shape[0]
         ell = _f64(np.broadcast_to(np.asarray(lengthscale, dtype=np.float64).reshape(-1), (d,)))
         if same_xz is None:
             same_xz = X.shape == Z.shape          # kernels.py:63
-        K = np.zeros((n, m), dtype=np.float64) if lower_only else np.empty((n, m), dtype=np.float64)
+        K = np.zeros((n, m), dtype=dt) if lower_only else np.empty((n, m), dtype=dt)
         if n == 0 or m == 0:
             return K
-        flags = FLAG_LOWER_ONLY if lower_only else 0
+        flags = (FLAG_LOWER_ONLY if lower_only else 0) | (FLAG_F32 if f32 else 0)
         self._check(self.lib.b2gp_gram(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), n, _ptr(Z), m, d,
                                        _ptr(ell), float(scale), float(period), float(diag_add), int(bool(same_xz)),
                                        _ptr(K), m, flags))
@@ -269,13 +279,16 @@ class Context:
 
     # ---- the posterior (host arrays in / out)
     def posterior(self, kind, Xtr, yres, Xnew, theta, noiseless=False, jitter=1e-6, want=("mean", "cov"),
-                  eps=None, timing=False, noise_vec=None):
+                  eps=None, timing=False, noise_vec=None, f32=False):
         """theta: [S, d+3] rows (lengthscale[d], k_scale, noise, period); yres [N] or [S, N].  Xtr [N, d] or per member
-        [S, N, d]; Xnew [P, d] or [S, P, d]; noise_vec None, [N] or [S, N] (per-point noise variances on k_XX's diagonal)."""
+        [S, N, d]; Xnew [P, d] or [S, P, d]; noise_vec None, [N] or [S, N] (per-point noise variances on k_XX's diagonal).
+        f32: the data arrays cross the boundary as float32 in both directions (B2GP_FLAG_F32), theta stays float64."""
+        _f64 = _f32 if f32 else globals()["_f64"]      # noqa: F811  data arrays in the I/O precision
+        odt = np.float32 if f32 else np.float64
         Xtr, Xnew = _f64(Xtr), _f64(Xnew)
         N, d = Xtr.shape[-2:]
         P = Xnew.shape[-2]
-        theta = _f64(theta).reshape(-1, d + 3)
+        theta = globals()["_f64"](theta).reshape(-1, d + 3)
         S = theta.shape[0]
         yres = _f64(yres)
         stride = 0 if yres.ndim == 1 else yres.shape[1]
@@ -286,23 +299,23 @@ class Context:
         for a, n_ in ((Xtr, xs), (Xnew, xns), (nv, nvs)):
             if a is not None and n_ and a.shape[0] != S:
                 raise ValueError("per-member arrays need a leading axis of length S = theta.shape[0]")
-        flags = 0
+        flags = FLAG_F32 if f32 else 0
         mean = var = cov = samp = None
         if "mean" in want:
             flags |= OUT_MEAN
-            mean = np.empty((S, P))
+            mean = np.empty((S, P), dtype=odt)
         if "var" in want:
             flags |= OUT_VAR
-            var = np.empty((S, P))
+            var = np.empty((S, P), dtype=odt)
         if "cov" in want:
             flags |= OUT_COV
-            cov = np.empty((S, P, P))
+            cov = np.empty((S, P, P), dtype=odt)
         n_samp = 0
         if eps is not None:
             eps = _f64(eps).reshape(S, -1, P)
             n_samp = eps.shape[1]
             flags |= OUT_SAMPLE
-            samp = np.empty((S, n_samp, P))
+            samp = np.empty((S, n_samp, P), dtype=odt)
         info = np.zeros(S, dtype=np.int32)
         t = Timing()
         self._check(self.lib.b2gp_posterior_batch(

@@ -49,6 +49,8 @@ struct Extra {  // ctx-private state that is not part of the struct the kernels'
     DevBuf gemm_buf[3];
     std::vector<void*> user_allocs;
     DevBuf eb[12];     // scratch of b2gp_sparse_elbo
+    DevBuf f32_in[8];  // fp32 staging of the inputs / outputs of calls made with B2GP_FLAG_F32
+    DevBuf f32_out[4];
     // factor cache of slot 0 (host-pointer, single-draw calls): predict_in_batches / viGP chunk loops call the
     // posterior repeatedly with the same training set and theta; the reference re-inverts k_XX every time
     // (gp.py:319-322 -> gp.py:269-271), here the factor L and its inverted diagonal blocks are kept.
@@ -57,7 +59,8 @@ struct Extra {  // ctx-private state that is not part of the struct the kernels'
         int kind = -1, d = 0;
         int64_t N = 0;
         double jitter = 0.0;
-        std::vector<double> theta, X;
+        std::vector<double> theta;
+        std::vector<char> X;   // raw bytes of the caller's training inputs (fp64 or fp32)
         int info = 0;
     } fcache;
     int64_t cache_hits = 0;
@@ -187,6 +190,8 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         cudaEventDestroy(ex->inputs_ready);
         free_buf(ex->theta1);
         for (auto& b : ex->eb) free_buf(b);
+        for (auto& b : ex->f32_in) free_buf(b);
+        for (auto& b : ex->f32_out) free_buf(b);
         free_buf(ex->potrf_buf);
         for (auto& b : ex->gemm_buf) free_buf(b);
         for (void* p : ex->user_allocs) cudaFree(p);
@@ -353,6 +358,63 @@ static int stage_in(b2gp_ctx* ctx, cudaStream_t st, DevBuf& buf, const void* src
     return B2GP_OK;
 }
 
+// ---- fp32 I/O (B2GP_FLAG_F32): the reference's default precision is float32 (gpax/utils/utils.py:19-21), so callers hand
+// over float arrays and expect float results.  Inputs are widened on the device right after the copy, outputs narrowed
+// right before it (round to nearest); the Gram builds, the factorisation and the solves stay fp64 in between.
+__global__ void cvt_f32_f64_kernel(double* __restrict__ dst, const float* __restrict__ src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = (double)src[i];
+}
+__global__ void cvt_f64_f32_kernel(float* __restrict__ dst, int64_t ldd, const double* __restrict__ src, int64_t lds, int64_t rows,
+                                   int64_t cols) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i % cols;
+        dst[r * ldd + c] = (float)src[r * lds + c];
+    }
+}
+static inline bool f32_io(unsigned flags) { return (flags & B2GP_FLAG_F32) != 0; }
+
+// stage_in for `count` elements that are doubles, or floats when f32: the result is always a device array of doubles
+static int stage_in_t(b2gp_ctx* ctx, cudaStream_t st, DevBuf& buf, DevBuf& tmp, const void* src, size_t count, bool is_dev, bool f32,
+                      const double** out) {
+    if (!f32) return stage_in(ctx, st, buf, src, count * 8, is_dev, out);
+    if (!src) {
+        *out = nullptr;
+        return B2GP_OK;
+    }
+    const float* fsrc = (const float*)src;
+    if (!is_dev) {
+        RET_IF(ensure(ctx, tmp, count * 4));
+        CUDA_TRY(ctx, cudaMemcpyAsync(tmp.p, src, count * 4, cudaMemcpyHostToDevice, st));
+        fsrc = (const float*)tmp.p;
+    }
+    RET_IF(ensure(ctx, buf, count * 8));
+    cvt_f32_f64_kernel<<<grid_for((int64_t)count), 256, 0, st>>>((double*)buf.p, fsrc, (int64_t)count);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    *out = (const double*)buf.p;
+    return B2GP_OK;
+}
+
+// device doubles [rows, cols] (leading dimension lds) -> the caller's float array (host or device, leading dimension ldd)
+static int store_out_f32(b2gp_ctx* ctx, cudaStream_t st, DevBuf& tmp, void* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows,
+                         int64_t cols, bool is_dev) {
+    if (rows <= 0 || cols <= 0) return B2GP_OK;
+    float* fdst = (float*)dst;
+    int64_t ldt = ldd;
+    if (!is_dev) {
+        RET_IF(ensure(ctx, tmp, (size_t)rows * cols * 4));
+        fdst = (float*)tmp.p;
+        ldt = cols;
+    }
+    cvt_f64_f32_kernel<<<grid_for(rows * cols), 256, 0, st>>>(fdst, ldt, src, lds, rows, cols);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    if (!is_dev)
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)ldd * 4, fdst, (size_t)ldt * 4, (size_t)cols * 4, (size_t)rows, cudaMemcpyDeviceToHost, st));
+    return B2GP_OK;
+}
+
 // ------------------------------------------------------------------------------------------ gram
 extern "C" int b2gp_gram(b2gp_ctx* ctx, int kind, const double* X, int64_t n, const double* Z, int64_t m, int d,
                          const double* lengthscale, double scale, double period, double diag_add, int same_xz, double* K,
@@ -375,24 +437,26 @@ extern "C" int b2gp_gram(b2gp_ctx* ctx, int kind, const double* X, int64_t n, co
     RET_IF(ensure(ctx, ex->theta1, sizeof th));
     CUDA_TRY(ctx, cudaMemcpyAsync(ex->theta1.p, th, (d + 3) * sizeof(double), cudaMemcpyHostToDevice, st));
     CUDA_TRY(ctx, cudaStreamSynchronize(st));  // th is a stack buffer
-    const bool dev = dev_ptrs(flags);
+    const bool dev = dev_ptrs(flags), f32 = f32_io(flags);
     const double *dX, *dZ;
-    RET_IF(stage_in(ctx, st, ctx->d_in[0], X, (size_t)n * d * 8, dev, &dX));
-    if (Z == X && !dev)
+    RET_IF(stage_in_t(ctx, st, ctx->d_in[0], ex->f32_in[0], X, (size_t)n * d, dev, f32, &dX));
+    if (Z == X && (!dev || f32))
         dZ = dX;
     else
-        RET_IF(stage_in(ctx, st, ctx->d_in[1], Z, (size_t)m * d * 8, dev, &dZ));
+        RET_IF(stage_in_t(ctx, st, ctx->d_in[1], ex->f32_in[1], Z, (size_t)m * d, dev, f32, &dZ));
     double* dK = K;
     int64_t ld = ldk;
-    if (!dev) {
+    if (!dev || f32) {
         ld = round_up(m, 2);
         RET_IF(ensure(ctx, ctx->d_out[0], (size_t)n * ld * 8));
         dK = (double*)ctx->d_out[0].p;
     }
     const int lower = (flags & B2GP_FLAG_LOWER_ONLY) && same_xz && n == m;
-    if (lower && !dev) CUDA_TRY(ctx, cudaMemsetAsync(dK, 0, (size_t)n * ld * 8, st));
+    if (lower && (!dev || f32)) CUDA_TRY(ctx, cudaMemsetAsync(dK, 0, (size_t)n * ld * 8, st));
     RET_IF(launch_gram(ctx, st, kind, dX, n, dZ, m, d, (const double*)ex->theta1.p, 1.0, 0.0, same_xz ? 1 : 0, lower, dK, ld));
-    if (!dev)
+    if (f32)
+        RET_IF(store_out_f32(ctx, st, ex->f32_out[0], K, ldk, dK, ld, n, m, dev));
+    else if (!dev)
         CUDA_TRY(ctx, cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ld * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
     RET_IF(tm.end(st, nullptr));
     ex->last.gram_bytes = 8.0 * (double)n * (double)m + 8.0 * (double)(n + m) * d;
@@ -551,7 +615,7 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
     ARG_CHECK(ctx, !want_samp || (eps && y_sampled && n_samp >= 1));
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Extra* ex = extra_of(ctx);
-    const bool dev = dev_ptrs(flags);
+    const bool dev = dev_ptrs(flags), f32 = f32_io(flags);
     const int nslots = (int)(S < ctx->n_streams ? S : ctx->n_streams);
     cudaStream_t st0 = ctx->slots[0].stream;
     CallTimer tm(ctx);
@@ -562,18 +626,19 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
     const int nth = d + 3;
     const double *dXtr, *dy, *dXnew, *dtheta, *deps = nullptr, *dnv = nullptr;
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, st0));
-    RET_IF(stage_in(ctx, st0, ctx->d_in[0], Xtr, (size_t)(xtr_stride ? S * xtr_stride : N * d) * 8, dev, &dXtr));
-    RET_IF(stage_in(ctx, st0, ctx->d_in[1], yres, (size_t)(yres_stride ? S * yres_stride : N) * 8, dev, &dy));
-    RET_IF(stage_in(ctx, st0, ctx->d_in[2], Xnew, (size_t)(xnew_stride ? S * xnew_stride : P * d) * 8, dev, &dXnew));
-    if (noise_vec) RET_IF(stage_in(ctx, st0, ctx->d_in[6], noise_vec, (size_t)(nv_stride ? S * nv_stride : N) * 8, dev, &dnv));
+    // with B2GP_FLAG_F32 the data arrays (X, y, X_new, noise_vec, eps) are floats; theta stays double
+    RET_IF(stage_in_t(ctx, st0, ctx->d_in[0], ex->f32_in[0], Xtr, (size_t)(xtr_stride ? S * xtr_stride : N * d), dev, f32, &dXtr));
+    RET_IF(stage_in_t(ctx, st0, ctx->d_in[1], ex->f32_in[1], yres, (size_t)(yres_stride ? S * yres_stride : N), dev, f32, &dy));
+    RET_IF(stage_in_t(ctx, st0, ctx->d_in[2], ex->f32_in[2], Xnew, (size_t)(xnew_stride ? S * xnew_stride : P * d), dev, f32, &dXnew));
+    if (noise_vec) RET_IF(stage_in_t(ctx, st0, ctx->d_in[6], ex->f32_in[6], noise_vec, (size_t)(nv_stride ? S * nv_stride : N), dev, f32, &dnv));
     RET_IF(stage_in(ctx, st0, ctx->d_in[3], theta, (size_t)S * nth * 8, dev, &dtheta));
-    if (want_samp) RET_IF(stage_in(ctx, st0, ctx->d_in[4], eps, (size_t)S * n_samp * P * 8, dev, &deps));
+    if (want_samp) RET_IF(stage_in_t(ctx, st0, ctx->d_in[4], ex->f32_in[4], eps, (size_t)S * n_samp * P, dev, f32, &deps));
     CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, st0));
     CUDA_TRY(ctx, cudaEventRecord(ex->inputs_ready, st0));
 
     // ---- outputs
     double *dmean = mean, *dvar = var, *dcov = cov, *dsamp = y_sampled;
-    if (!dev) {
+    if (!dev || f32) {
         if (want_mean) {
             RET_IF(ensure(ctx, ctx->d_out[0], (size_t)S * P * 8));
             dmean = (double*)ctx->d_out[0].p;
@@ -637,8 +702,9 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
     const bool cacheable = (S == 1 && !dev && !noise_vec);
     if (cacheable) {
         auto& fc = ex->fcache;
-        reuse = fc.valid && fc.kind == kind && fc.N == N && fc.d == d && fc.jitter == jitter &&
-                memcmp(fc.theta.data(), theta, (size_t)nth * 8) == 0 && memcmp(fc.X.data(), Xtr, (size_t)N * d * 8) == 0;
+        const size_t xbytes = (size_t)N * d * (f32 ? 4 : 8);
+        reuse = fc.valid && fc.kind == kind && fc.N == N && fc.d == d && fc.jitter == jitter && fc.X.size() == xbytes &&
+                memcmp(fc.theta.data(), theta, (size_t)nth * 8) == 0 && memcmp(fc.X.data(), Xtr, xbytes) == 0;
         if (reuse) ex->cache_hits++;
     }
     ex->fcache.valid = false;
@@ -770,7 +836,12 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
     CUDA_TRY(ctx, cudaEventRecord(ev_c, st0));
     std::vector<int> hinfo((size_t)2 * S);
     CUDA_TRY(ctx, cudaMemcpyAsync(hinfo.data(), dinfo, (size_t)2 * S * sizeof(int), cudaMemcpyDeviceToHost, st0));
-    if (!dev) {
+    if (f32) {
+        if (want_mean) RET_IF(store_out_f32(ctx, st0, ex->f32_out[0], mean, P, dmean, P, S, P, dev));
+        if (want_var) RET_IF(store_out_f32(ctx, st0, ex->f32_out[1], var, P, dvar, P, S, P, dev));
+        if (want_cov) RET_IF(store_out_f32(ctx, st0, ex->f32_out[2], cov, P, dcov, P, S * P, P, dev));
+        if (want_samp) RET_IF(store_out_f32(ctx, st0, ex->f32_out[3], y_sampled, P, dsamp, P, S * n_samp, P, dev));
+    } else if (!dev) {
         if (want_mean) CUDA_TRY(ctx, cudaMemcpyAsync(mean, dmean, (size_t)S * P * 8, cudaMemcpyDeviceToHost, st0));
         if (want_var) CUDA_TRY(ctx, cudaMemcpyAsync(var, dvar, (size_t)S * P * 8, cudaMemcpyDeviceToHost, st0));
         if (want_cov) CUDA_TRY(ctx, cudaMemcpyAsync(cov, dcov, (size_t)S * P * P * 8, cudaMemcpyDeviceToHost, st0));
@@ -788,7 +859,7 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
             fc.d = d;
             fc.jitter = jitter;
             fc.theta.assign(theta, theta + nth);
-            fc.X.assign(Xtr, Xtr + (size_t)N * d);
+            fc.X.assign((const char*)Xtr, (const char*)Xtr + (size_t)N * d * (f32 ? 4 : 8));
             fc.info = hinfo[0];
         }
         fc.valid = true;
@@ -999,7 +1070,7 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     ARG_CHECK(ctx, !want_cov || cov);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Extra* ex = extra_of(ctx);
-    const bool dev = dev_ptrs(flags);
+    const bool dev = dev_ptrs(flags), f32 = f32_io(flags);
     Slot& sl = ctx->slots[0];
     cudaStream_t st = sl.stream;
     ex->fcache.valid = false;
@@ -1007,11 +1078,11 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     RET_IF(tm.begin(st));
     const int nth = d + 3;
     const double *dXu, *dXtr, *dy, *dXnew, *dth;
-    RET_IF(stage_in(ctx, st, ctx->d_in[0], Xtr, (size_t)N * d * 8, dev, &dXtr));
-    RET_IF(stage_in(ctx, st, ctx->d_in[1], yres, (size_t)N * 8, dev, &dy));
-    RET_IF(stage_in(ctx, st, ctx->d_in[2], Xnew, (size_t)P * d * 8, dev, &dXnew));
+    RET_IF(stage_in_t(ctx, st, ctx->d_in[0], ex->f32_in[0], Xtr, (size_t)N * d, dev, f32, &dXtr));
+    RET_IF(stage_in_t(ctx, st, ctx->d_in[1], ex->f32_in[1], yres, (size_t)N, dev, f32, &dy));
+    RET_IF(stage_in_t(ctx, st, ctx->d_in[2], ex->f32_in[2], Xnew, (size_t)P * d, dev, f32, &dXnew));
     RET_IF(stage_in(ctx, st, ctx->d_in[3], theta, (size_t)nth * 8, dev, &dth));
-    RET_IF(stage_in(ctx, st, ctx->d_in[5], Xu, (size_t)M * d * 8, dev, &dXu));
+    RET_IF(stage_in_t(ctx, st, ctx->d_in[5], ex->f32_in[5], Xu, (size_t)M * d, dev, f32, &dXu));
     double noise_h = 0.0;
     if (dev) {
         CUDA_TRY(ctx, cudaMemcpyAsync(&noise_h, dth + d + 1, 8, cudaMemcpyDeviceToHost, st));
@@ -1023,7 +1094,7 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     RET_IF(ensure(ctx, sl.A, (size_t)2 * M * ldM * 8));
     RET_IF(ensure(ctx, sl.Linv, (size_t)2 * linv_bytes(M)));
     RET_IF(ensure(ctx, ctx->d_out[0], (size_t)(2 * P + M + 16) * 8));
-    if (want_cov && !dev) RET_IF(ensure(ctx, ctx->d_out[2], (size_t)P * ldC * 8));
+    if (want_cov && (!dev || f32)) RET_IF(ensure(ctx, ctx->d_out[2], (size_t)P * ldC * 8));
     RET_IF(ensure(ctx, ctx->d_info, 64));
     int* dinfo = (int*)ctx->d_info.p;
     CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 16, st));
@@ -1035,17 +1106,23 @@ extern "C" int b2gp_sparse_posterior(b2gp_ctx* ctx, int kind, const double* Xu, 
     double* vv = mv + P;
     double* cvec = vv + P;
     RET_IF(sparse_partial_dev(ctx, sl, kind, dXu, M, dXtr, N, dy, d, dth, jitter, noise_h, Luu, ldM, LinvU, Kmat, ldM, cvec, dinfo));
-    double* dmean = (want_mean && dev) ? mean : mv;
-    double* dvar = (want_var && dev) ? var : vv;
-    double* C = dev ? cov : (double*)ctx->d_out[2].p;
-    const int64_t ldc = dev ? P : ldC;
+    const bool direct = dev && !f32;     // results written straight into the caller's (device, fp64) arrays
+    double* dmean = (want_mean && direct) ? mean : mv;
+    double* dvar = (want_var && direct) ? var : vv;
+    double* C = direct ? cov : (double*)ctx->d_out[2].p;
+    const int64_t ldc = direct ? P : ldC;
     RET_IF(sparse_finish_dev(ctx, sl, kind, dXu, M, Luu, ldM, LinvU, Kmat, ldM, LinvK, cvec, dXnew, P, d, dth, noiseless, jitter,
                              want_var, want_cov, dmean, dvar, C, ldc, dinfo));
-    if (want_cov && !dev)
+    if (want_cov && f32)
+        RET_IF(store_out_f32(ctx, st, ex->f32_out[2], cov, P, C, ldc, P, P, dev));
+    else if (want_cov && !dev)
         CUDA_TRY(ctx, cudaMemcpy2DAsync(cov, (size_t)P * 8, C, (size_t)ldc * 8, (size_t)P * 8, (size_t)P, cudaMemcpyDeviceToHost, st));
     int hinfo[2] = {0, 0};
     CUDA_TRY(ctx, cudaMemcpyAsync(hinfo, dinfo, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (!dev) {
+    if (f32) {
+        if (want_mean) RET_IF(store_out_f32(ctx, st, ex->f32_out[0], mean, P, dmean, P, 1, P, dev));
+        if (want_var) RET_IF(store_out_f32(ctx, st, ex->f32_out[1], var, P, dvar, P, 1, P, dev));
+    } else if (!dev) {
         if (want_mean) CUDA_TRY(ctx, cudaMemcpyAsync(mean, dmean, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
         if (want_var) CUDA_TRY(ctx, cudaMemcpyAsync(var, dvar, (size_t)P * 8, cudaMemcpyDeviceToHost, st));
     }

@@ -15,7 +15,9 @@ kernel_fn_type = Callable[[np.ndarray, np.ndarray, Dict[str, np.ndarray], np.nda
 
 
 def _as2d(X):
-    X = np.asarray(X, dtype=np.float64)
+    X = np.asarray(X)
+    if X.dtype != np.float32:                       # float32 inputs keep their precision across the boundary (B2GP_FLAG_F32)
+        X = X.astype(np.float64, copy=False)
     return X if X.ndim > 1 else X[:, None]
 
 
@@ -35,7 +37,8 @@ def _gram(kind, X, Z, params, noise, jitter, ctx=None):
     period = 1.0 if period is None else _scalar(period, "period")
     same = X.shape == Z.shape                       # kernels.py:63 -- shape equality, not identity
     diag = _scalar(noise, "noise") + float(jitter)  # kernels.py:24-25, 64
-    return ctx.gram(kind, X, Z, params["k_length"], _scalar(params["k_scale"], "k_scale"), period, diag, same)
+    f32 = np.asarray(X).dtype == np.float32 and np.asarray(Z).dtype == np.float32      # the reference's default precision
+    return ctx.gram(kind, X, Z, params["k_length"], _scalar(params["k_scale"], "k_scale"), period, diag, same, f32=f32)
 
 
 def RBFKernel(X, Z, params, noise=0, jitter=1e-6, **kwargs):

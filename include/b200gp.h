@@ -49,6 +49,10 @@ enum {
 enum {
     B2GP_FLAG_DEVICE_PTRS = 1u << 0, /* array arguments are device pointers                                  */
     B2GP_FLAG_LOWER_ONLY  = 1u << 1, /* b2gp_gram with same_xz: write only the lower triangle (j <= i)       */
+    B2GP_FLAG_F32         = 1u << 2, /* b2gp_gram / b2gp_posterior(_batch) / b2gp_sparse_posterior: the DATA arrays (X, Z, y, X_new, Xu,
+                                        noise_vec, eps in; K, mean, var, cov, y_sampled out) are float, the reference's default
+                                        precision (gpax/utils/utils.py:19-21); theta stays double.  Widened / narrowed on the
+                                        device, everything in between is fp64                                  */
     B2GP_OUT_MEAN         = 1u << 4, /* b2gp_posterior: produce mean[S,P]                                    */
     B2GP_OUT_VAR          = 1u << 5, /* ... var[S,P] = diag(cov)     (viGP.predict, vigp.py:184-185)         */
     B2GP_OUT_COV          = 1u << 6, /* ... cov[S,P,P]               (get_mvn_posterior, gp.py:272)          */

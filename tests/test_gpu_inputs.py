@@ -50,3 +50,35 @@ def test_bad_arguments_raise():
     m.X_train, m.y_train = np.zeros((5, 2)), np.zeros(5)
     with pytest.raises(ValueError):
         m.get_mvn_posterior(np.zeros((3, 2)), {"k_length": np.ones(3), "k_scale": 1.0, "noise": 0.1})
+
+
+def test_fp32_io_matches_fp32_rounded_oracle():
+    """B2GP_FLAG_F32 (the reference's default precision, gpax/utils/utils.py:19-21): float32 arrays in and out of the C-ABI,
+    fp64 in between -- the result is the fp64 posterior of the float32-rounded inputs, rounded once to float32."""
+    import gpax_b200
+    import oracle
+    rng = np.random.default_rng(12)
+    N, P, d = 900, 70, 2
+    X = rng.uniform(0, 1, (N, d)).astype(np.float32)
+    y = (np.sin(5 * X[:, 0]) + X[:, 1]).astype(np.float32)
+    Xn = rng.uniform(0, 1, (P, d)).astype(np.float32)
+    params = {"k_length": np.array([0.3, 0.4]), "k_scale": 1.2, "noise": 0.05}
+    for kname in ("RBF", "Matern"):
+        rmean, rcov = oracle.exact_posterior_chol(X.astype(np.float64), y.astype(np.float64), Xn.astype(np.float64), params, kname)
+        m = gpax_b200.ExactGP(d, kname)
+        m.X_train, m.y_train = X, y
+        mean, cov = m.get_mvn_posterior(Xn, params)
+        assert mean.dtype == np.float32 and cov.dtype == np.float32
+        np.testing.assert_array_equal(mean, rmean.astype(np.float32))
+        np.testing.assert_allclose(cov, rcov.astype(np.float32), rtol=0, atol=6e-8 * np.abs(rcov).max())   # one float32 rounding of entries that cancel
+        K = gpax_b200.get_kernel(kname)(X, X, params, 0.05)
+        assert K.dtype == np.float32
+        ref = oracle.get_kernel(kname)(X.astype(np.float64), X.astype(np.float64), params, 0.05).astype(np.float32)
+        np.testing.assert_array_equal(K, ref)
+    v = gpax_b200.viGP(d, "RBF")
+    v.X_train, v.y_train = X, y
+    vm, vv = v.predict(None, Xn, samples=params)
+    assert vm.dtype == np.float32 and vv.dtype == np.float32
+    ctx = m.ctx
+    out = ctx.posterior("RBF", X, y, Xn, np.array([[0.3, 0.4, 1.2, 0.05, 1.0]]), want=("mean", "var"), f32=True)
+    np.testing.assert_array_equal(out["mean"][0], vm)
