@@ -2077,11 +2077,26 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     cudaEvent_t ev_f0 = ctx->slots[0].ev[2], ev_f1 = ctx->slots[0].ev[3];
     CUDA_TRY(ctx, cudaEventRecord(ev_f0, cs));
 
+    // optional phase profile (B2GP_DIST_PROF=1): CUDA events on both streams, summed per phase after the call
+    const bool prof = getenv("B2GP_DIST_PROF") != nullptr;
+    enum { PH_SLICE, PH_G1, PH_POTRF, PH_UWAIT, PH_PANEL, PH_G2, PH_COMMWAIT, PH_UBCAST, PH_ROWBCAST, PH_ALLGATHER, PH_N };
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pev[PH_N];
+    auto mark = [&](cudaStream_t s) -> cudaEvent_t {
+        if (!prof) return nullptr;
+        cudaEvent_t e = ex->pool.get();
+        cudaEventRecord(e, s);
+        return e;
+    };
+    auto span = [&](int ph, cudaEvent_t a, cudaEvent_t b) {
+        if (prof && a && b) pev[ph].emplace_back(a, b);
+    };
+
     // ---- panel pipeline pieces
     auto panel_front = [&](int64_t k) -> int {   // (a) .. (f) of step k; compute parts on cs, collectives on ms
         const int kr = (int)(k % pr), kc = (int)(k % pc);
         const int64_t li0 = g.first_row_after(k, myrow), rows = g.panel_rows(k, myrow), slot = g.slot_rows(k);
         double* PBk = (double*)ds->PB[k & 1].p;
+        cudaEvent_t p0 = mark(cs);
         if (mycol == kc) {
             if (myrow == kr) {
                 double* D = A + ((k / pr) * nb) * ld + (k / pc) * nb;
@@ -2091,13 +2106,19 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
                 ctx->launches++;
                 RET_IF(trsm_rec(ctx, cs, UB, nb, nb, D, ld, nb, (const double*)ds->linv.p));      // U = L_kk^{-T}
             }
+            cudaEvent_t p1 = mark(cs);
+            span(PH_POTRF, p0, p1);
             if (pr > 1) {
                 CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, cs));
                 CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_u, 0));
+                cudaEvent_t m0 = mark(ms);
                 NCCL_TRY(ctx, nc->Broadcast(UB, UB, (size_t)(nb * nb), ncclDouble, kr, ds->colc, ms));
+                span(PH_UBCAST, m0, mark(ms));
                 CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc, ms));
                 CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
             }
+            p0 = mark(cs);
+            span(PH_UWAIT, p1, p0);
             if (rows > 0) {
                 double* rp = A + (li0 * nb) * ld + (k / pc) * nb;
                 RET_IF(ozaki_dispatch(ctx, cs, rows, nb, nb, 1.0, rp, ld, UB, nb, rp, ld, false, true, true, true));
@@ -2105,13 +2126,18 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
                 CUDA_TRY(ctx, cudaGetLastError());
                 ctx->launches++;
             }
+            span(PH_PANEL, p0, mark(cs));
         }
         if (slot > 0) {
             CUDA_TRY(ctx, cudaEventRecord(ds->ev_chunk, cs));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_chunk, 0));
             double* mine = PBk + (int64_t)myrow * slot * nb;
+            cudaEvent_t m0 = mark(ms);
             if (pc > 1) NCCL_TRY(ctx, nc->Broadcast(mine, mine, (size_t)(slot * nb), ncclDouble, kc, ds->rowc, ms));
+            cudaEvent_t m1 = mark(ms);
+            span(PH_ROWBCAST, m0, m1);
             if (pr > 1) NCCL_TRY(ctx, nc->AllGather(mine, PBk, (size_t)(slot * nb), ncclDouble, ds->colc, ms));
+            span(PH_ALLGATHER, m1, mark(ms));
         }
         CUDA_TRY(ctx, cudaEventRecord(ds->ev_comm[k & 1], ms));
         return B2GP_OK;
@@ -2147,11 +2173,19 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     // ---- the factorisation (with the right-hand-side rows riding below)
     RET_IF(panel_front(0));
     for (int64_t k = 0; k < T; ++k) {
+        cudaEvent_t q0 = mark(cs);
         CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_comm[k & 1], 0));
+        cudaEvent_t q1 = mark(cs);
+        span(PH_COMMWAIT, q0, q1);
         RET_IF(update_slices(k));
+        cudaEvent_t q2 = mark(cs);
+        span(PH_SLICE, q1, q2);
         RET_IF(update_part(k, 1));
+        span(PH_G1, q2, mark(cs));
         if (k + 1 < T) RET_IF(panel_front(k + 1));
+        cudaEvent_t q3 = mark(cs);
         RET_IF(update_part(k, 2));
+        span(PH_G2, q3, mark(cs));
     }
     CUDA_TRY(ctx, cudaEventRecord(ev_f1, cs));
 
@@ -2198,6 +2232,22 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     float ms_f = 0.f;
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms_f, ev_f0, ev_f1));
     ex->last.potrf_ms = ms_f;
+    if (prof) {
+        static const char* names[PH_N] = {"update slices", "g1 (next tile column)", "diag potrf + U", "wait for U broadcast", "panel solve + pack",
+                                          "g2 (rest of the update)", "wait for the panel exchange", "[comm stream] U broadcast",
+                                          "[comm stream] panel row broadcast", "[comm stream] panel column all-gather"};
+        fprintf(stderr, "[dist prof] rank %d (%d,%d) N=%lld nb=%lld factorisation %.2f ms:", ds->rank, myrow, mycol, (long long)N, (long long)nb, ms_f);
+        for (int ph = 0; ph < PH_N; ++ph) {
+            double tot = 0.0;
+            for (auto& pe : pev[ph]) {
+                float f = 0.f;
+                cudaEventElapsedTime(&f, pe.first, pe.second);
+                tot += f;
+            }
+            fprintf(stderr, " %s %.2f;", names[ph], tot);
+        }
+        fprintf(stderr, "\n");
+    }
     const double n = (double)N, p = (double)P;
     ex->last.flops = n * n * n / 3.0 + n * n * (p + 1.0) + 4.0 * n * p;
     if (timing) *timing = ex->last;
