@@ -252,7 +252,9 @@ def dist_workloads(ctx, ffi, rank, world, local, td, steps=3):
     theta = np.array([0.3, 0.3, 0.3, 1.0, 0.1, 1.0])
     dc = None
     if world > 1:
-        dc = dist.DistContext(ctx=ctx, rank=rank, world=world)
+        grid = os.environ.get("B200GP_C4_GRID")                 # e.g. "4x2"; default: dist.default_grid (2 x 4 on 8 GPUs)
+        dc = dist.DistContext(ctx=ctx, rank=rank, world=world, grid=tuple(int(v) for v in grid.split("x")) if grid else None)
+        nb = int(os.environ.get("B200GP_C4_NB", nb))
 
     def timed(fn):
         fn()                                   # warm-up: allocations, tile lists, NCCL channels

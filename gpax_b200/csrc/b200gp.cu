@@ -2092,10 +2092,8 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     };
 
     // ---- panel pipeline pieces
-    auto panel_front = [&](int64_t k) -> int {   // (a) .. (f) of step k; compute parts on cs, collectives on ms
+    auto panel_front_a = [&](int64_t k) -> int {   // (a), (b) of step k: diagonal tile on its owner, U on its way down the column
         const int kr = (int)(k % pr), kc = (int)(k % pc);
-        const int64_t li0 = g.first_row_after(k, myrow), rows = g.panel_rows(k, myrow), slot = g.slot_rows(k);
-        double* PBk = (double*)ds->PB[k & 1].p;
         cudaEvent_t p0 = mark(cs);
         if (mycol == kc) {
             if (myrow == kr) {
@@ -2115,9 +2113,18 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
                 NCCL_TRY(ctx, nc->Broadcast(UB, UB, (size_t)(nb * nb), ncclDouble, kr, ds->colc, ms));
                 span(PH_UBCAST, m0, mark(ms));
                 CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc, ms));
-                CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
             }
-            p0 = mark(cs);
+        }
+        return B2GP_OK;
+    };
+    auto panel_front_b = [&](int64_t k) -> int {   // (c) .. (f) of step k: panel solve once U is here, pack, panel exchange
+        const int kc = (int)(k % pc);
+        const int64_t li0 = g.first_row_after(k, myrow), rows = g.panel_rows(k, myrow), slot = g.slot_rows(k);
+        double* PBk = (double*)ds->PB[k & 1].p;
+        if (mycol == kc) {
+            cudaEvent_t p1 = mark(cs);
+            if (pr > 1) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
+            cudaEvent_t p0 = mark(cs);
             span(PH_UWAIT, p1, p0);
             if (rows > 0) {
                 double* rp = A + (li0 * nb) * ld + (k / pc) * nb;
@@ -2171,7 +2178,31 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     };
 
     // ---- the factorisation (with the right-hand-side rows riding below)
-    RET_IF(panel_front(0));
+    // Program order of one step on the compute stream.  The owner of the next diagonal tile factors it right after g1; the
+    // other ranks of its process column have nothing to do until U arrives, so THEY run the bulk update g2 first (it
+    // overlaps the owner's latency-bound factorisation); ranks of other columns only feed the exchange.
+    auto panel_front = [&](int64_t k, int64_t upd_k) -> int {
+        const bool in_col = (mycol == (int)(k % pc)), owner = in_col && (myrow == (int)(k % pr));
+        RET_IF(panel_front_a(k));
+        const bool g2_first = upd_k >= 0 && in_col && !owner && pr > 1;
+        cudaEvent_t q3 = nullptr;
+        if (g2_first) {
+            q3 = mark(cs);
+            RET_IF(update_part(upd_k, 2));
+            span(PH_G2, q3, mark(cs));
+        }
+        RET_IF(panel_front_b(k));
+        if (upd_k >= 0 && !g2_first) {
+            q3 = mark(cs);
+            RET_IF(update_part(upd_k, 2));
+            span(PH_G2, q3, mark(cs));
+        }
+        return B2GP_OK;
+    };
+    // the persistent int8 kernels leave a few SMs to the NCCL kernels of the exchange running beside them
+    const int big_grid_saved = ctx->big_grid;
+    if (ds->nranks > 1 && ctx->big_grid == 0) ctx->big_grid = ctx->sm_count - 16;
+    RET_IF(panel_front(0, -1));
     for (int64_t k = 0; k < T; ++k) {
         cudaEvent_t q0 = mark(cs);
         CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_comm[k & 1], 0));
@@ -2182,11 +2213,15 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
         span(PH_SLICE, q1, q2);
         RET_IF(update_part(k, 1));
         span(PH_G1, q2, mark(cs));
-        if (k + 1 < T) RET_IF(panel_front(k + 1));
-        cudaEvent_t q3 = mark(cs);
-        RET_IF(update_part(k, 2));
-        span(PH_G2, q3, mark(cs));
+        if (k + 1 < T) {
+            RET_IF(panel_front(k + 1, k));
+        } else {
+            cudaEvent_t q3 = mark(cs);
+            RET_IF(update_part(k, 2));
+            span(PH_G2, q3, mark(cs));
+        }
     }
+    ctx->big_grid = big_grid_saved;
     CUDA_TRY(ctx, cudaEventRecord(ev_f1, cs));
 
     // ---- epilogue: mean[p] = <V[p, :], w>, var[p] = k(x,x) + noise_p + jitter - |V[p, :]|^2, summed over the process grid
