@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libb200gp.so")
 
 KERNEL_RBF, KERNEL_MATERN52, KERNEL_PERIODIC = 0, 1, 2
+KERNEL_NNGP_ERF, KERNEL_NNGP_RELU = 3, 4
 KIND = {"RBF": KERNEL_RBF, "Matern": KERNEL_MATERN52, "Periodic": KERNEL_PERIODIC}
 
 FLAG_DEVICE_PTRS = 1 << 0

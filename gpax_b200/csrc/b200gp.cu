@@ -420,7 +420,7 @@ extern "C" int b2gp_gram(b2gp_ctx* ctx, int kind, const double* X, int64_t n, co
                          const double* lengthscale, double scale, double period, double diag_add, int same_xz, double* K,
                          int64_t ldk, unsigned flags) {
     if (!ctx) return B2GP_ERR_ARG;
-    ARG_CHECK(ctx, kind >= 0 && kind <= 2);
+    ARG_CHECK(ctx, kind >= 0 && kind <= B2GP_KERNEL_NNGP_RELU);
     ARG_CHECK(ctx, X && Z && K && lengthscale);
     ARG_CHECK(ctx, n >= 0 && m >= 0 && d >= 1 && d <= GRAM_MAX_D && ldk >= m);
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

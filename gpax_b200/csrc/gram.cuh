@@ -46,6 +46,32 @@ __device__ __forceinline__ double cov_from_r2(int kind, double r2, double scale)
     return scale * (1.0 + s5r + (5.0 / 3.0) * r2) * exp(-s5r);
 }
 
+// NNGP kernels (gpax/kernels/kernels.py:120-183): the infinite-width-network recursion on the three inner products of a
+// pair, `depth` times; erf activation (kernels.py:145-151) or ReLU (kernels.py:176-183).
+__device__ __forceinline__ double nngp_step(bool relu, double a, double b, double c, double var_b, double var_w) {
+    if (!relu) {
+        double fr = 2.0 * a / sqrt((1.0 + 2.0 * b) * (1.0 + 2.0 * c));
+        fr = fmin(fmax(fr, -1.0 + 1e-7), 1.0 - 1e-7);
+        return var_b + 2.0 * var_w / 3.141592653589793 * asin(fr);
+    }
+    const double s = sqrt(b * c);
+    const double fr = a / s;
+    const double th = acos(fmin(fmax(fr, -1.0 + 1e-7), 1.0 - 1e-7));
+    return var_b + var_w / (2.0 * 3.141592653589793) * s * (sin(th) + (3.141592653589793 - th) * fr);
+}
+__device__ __forceinline__ double nngp_pair(bool relu, double xz, double xx, double zz, int d, double var_b, double var_w, int depth) {
+    double k12 = var_b + var_w * xz / d, k11 = var_b + var_w * xx / d, k22 = var_b + var_w * zz / d;   // depth 0, kernels.py:139-140
+    for (int l = 0; l < depth; ++l) {
+        const double n12 = nngp_step(relu, k12, k11, k22, var_b, var_w);
+        const double n11 = nngp_step(relu, k11, k11, k11, var_b, var_w);
+        const double n22 = nngp_step(relu, k22, k22, k22, var_b, var_w);
+        k12 = n12;
+        k11 = n11;
+        k22 = n22;
+    }
+    return k12;
+}
+
 __global__ void __launch_bounds__(GRAM_THREADS) gram_kernel(const GramArgs p) {
     extern __shared__ __align__(16) double sm[];
     // layout: Xs[GRAM_BM][d] | x2[GRAM_BM] | Zt[d][GRAM_BN] | z2[GRAM_BN] | ell[d]
@@ -60,6 +86,7 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram_kernel(const GramArgs p) {
     const int64_t col0 = (int64_t)blockIdx.x * GRAM_BN;
     if (p.lower_only && col0 > row0 + GRAM_BM - 1) return;
     const int tid = threadIdx.x;
+    const bool nngp = (p.kind == B2GP_KERNEL_NNGP_ERF || p.kind == B2GP_KERNEL_NNGP_RELU);
     const bool periodic = (p.kind == B2GP_KERNEL_PERIODIC);
 
     if (tid < d) ell[tid] = p.theta[tid];
@@ -73,13 +100,13 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram_kernel(const GramArgs p) {
         const int r = idx / d, k = idx % d;
         const int64_t gr = row0 + r;
         double v = (gr < p.n) ? p.X[gr * d + k] : 0.0;
-        Xs[r * d + k] = periodic ? v : v / ell[k];
+        Xs[r * d + k] = (periodic || nngp) ? v : v / ell[k];
     }
     for (int idx = tid; idx < GRAM_BN * d; idx += GRAM_THREADS) {
         const int c = idx / d, k = idx % d;
         const int64_t gc = col0 + c;
         double v = (gc < p.m) ? p.Z[gc * d + k] : 0.0;
-        Zt[k * GRAM_BN + c] = periodic ? v : v / ell[k];
+        Zt[k * GRAM_BN + c] = (periodic || nngp) ? v : v / ell[k];
     }
     __syncthreads();
     if (!periodic) {
@@ -118,12 +145,19 @@ __global__ void __launch_bounds__(GRAM_THREADS) gram_kernel(const GramArgs p) {
                 xz0 = fma(x, Zt[k * GRAM_BN + cl], xz0);
                 xz1 = fma(x, Zt[k * GRAM_BN + cl + 1], xz1);
             }
-            double r20 = (x2[rl] - 2.0 * xz0) + z2[cl];       // kernels.py:40
-            double r21 = (x2[rl] - 2.0 * xz1) + z2[cl + 1];
-            r20 = r20 < 0.0 ? 0.0 : r20;                      // kernels.py:41 (clip(0); NaN stays NaN)
-            r21 = r21 < 0.0 ? 0.0 : r21;
-            v0 = cov_from_r2(p.kind, r20, scale);
-            v1 = cov_from_r2(p.kind, r21, scale);
+            if (nngp) {   // theta: [0] = depth, [d] = var_w, [d+2] = var_b
+                const bool relu = p.kind == B2GP_KERNEL_NNGP_RELU;
+                const int depth = (int)ell[0];
+                v0 = nngp_pair(relu, xz0, x2[rl], z2[cl], d, period, scale, depth);
+                v1 = nngp_pair(relu, xz1, x2[rl], z2[cl + 1], d, period, scale, depth);
+            } else {
+                double r20 = (x2[rl] - 2.0 * xz0) + z2[cl];       // kernels.py:40
+                double r21 = (x2[rl] - 2.0 * xz1) + z2[cl + 1];
+                r20 = r20 < 0.0 ? 0.0 : r20;                      // kernels.py:41 (clip(0); NaN stays NaN)
+                r21 = r21 < 0.0 ? 0.0 : r21;
+                v0 = cov_from_r2(p.kind, r20, scale);
+                v1 = cov_from_r2(p.kind, r21, scale);
+            }
         } else {
             double s0 = 0.0, s1 = 0.0;
             for (int k = 0; k < d; ++k) {

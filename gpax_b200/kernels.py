@@ -60,14 +60,33 @@ _BOOK = {"RBF": RBFKernel, "Matern": MaternKernel, "Periodic": PeriodicKernel}
 _NAME_OF = {RBFKernel: "RBF", MaternKernel: "Matern", PeriodicKernel: "Periodic"}
 
 
+def NNGPKernel(activation: str = "erf", depth: int = 3):
+    """Neural-network GP kernel (gpax/kernels/kernels.py:186-224): returns k(X, Z, params, noise, jitter) with
+    params = {"var_b", "var_w"}; the recursion over `depth` layers runs in the fused Gram kernel on the GPU."""
+    kind = _ffi.KERNEL_NNGP_RELU if activation == "relu" else _ffi.KERNEL_NNGP_ERF
+
+    def NNGPKernel_func(X, Z, params, noise=0, jitter=1e-6, **kwargs):
+        X, Z = _as2d(X), _as2d(Z)
+        ctx = kwargs.get("ctx") or _ffi.default_context()
+        same = X.shape == Z.shape                                    # kernels.py:221
+        f32 = X.dtype == np.float32 and Z.dtype == np.float32
+        ell = np.full(X.shape[1], float(depth))                      # lengthscale slot 0 carries the depth
+        return ctx.gram(kind, X, Z, ell, _scalar(params["var_w"], "var_w"), _scalar(params["var_b"], "var_b"),
+                        _scalar(noise, "noise") + float(jitter), same, f32=f32)
+    return NNGPKernel_func
+
+
 def get_kernel(kernel: Union[str, kernel_fn_type] = "RBF", **kwargs):
-    """Name -> function; callables pass through (gpax/kernels/kernels.py:227-241).  The reference's
-    fourth entry, 'NNGP', is outside the hot path and raises KeyError here."""
+    """Name -> function; callables pass through (gpax/kernels/kernels.py:225-241).  'NNGP' takes activation= / depth=
+    through **kwargs as in the reference; it is a Gram-only kernel here (non-stationary), so models built on it go
+    through the callable-kernel posterior (host-supplied Gram matrices, GPU factorisation and solves)."""
     if isinstance(kernel, str):
+        if kernel == "NNGP":
+            return NNGPKernel(**kwargs)
         try:
             kernel = _BOOK[kernel]
         except KeyError:
-            print("Select one of the currently available kernels:", *_BOOK.keys())
+            print("Select one of the currently available kernels:", *_BOOK.keys(), "NNGP")
             raise
     return kernel
 

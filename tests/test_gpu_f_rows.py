@@ -214,3 +214,26 @@ def test_variant_fits_run(gp):
     dv = h.get_data_var_samples()
     assert dv.shape == (30, 60) and np.isfinite(dv).all()
     assert np.median(dv[:, 45:]) > np.median(dv[:, :15])            # the inferred noise grows with x, as the data's does
+
+
+def test_nngp_kernel_golden(gp, gf):
+    """gpax/kernels/kernels.py:120-224 in the fused Gram kernel (kinds 3 / 4), and a posterior through the callable path"""
+    prm = {"var_b": 0.3, "var_w": 1.7}
+    for act in ("erf", "relu"):
+        for depth in (1, 3):
+            k = gp.get_kernel("NNGP", activation=act, depth=depth)
+            np.testing.assert_allclose(k(gf["nngp_X"], gf["nngp_Z"], prm, 0.05), gf[f"nngp_{act}_d{depth}_XZ"], rtol=1e-11)
+            np.testing.assert_allclose(k(gf["nngp_X"], gf["nngp_X"], prm, 0.05), gf[f"nngp_{act}_d{depth}_XX"], rtol=1e-11)
+    from oracle import variants_oracle as vo
+    rng = np.random.default_rng(1)
+    X, Xn = rng.standard_normal((400, 3)), rng.standard_normal((30, 3))
+    y = np.tanh(X @ np.array([0.5, -0.3, 0.8])) + 0.05 * rng.standard_normal(400)
+    m = gp.ExactGP(3, gp.get_kernel("NNGP", activation="erf", depth=2))
+    m.X_train, m.y_train = X, y
+    params = {"var_b": 0.2, "var_w": 1.5, "noise": 0.05}
+    mean, cov = m.get_mvn_posterior(Xn, params)
+    kf = lambda A, B, n=0.0, j=1e-6: vo.nngp_kernel(A, B, params, n, j, "erf", 2)   # noqa: E731
+    Kinv = np.linalg.inv(kf(X, X, 0.05))
+    kpx = kf(Xn, X, 0.0, 0.0)
+    assert_close(mean, kpx @ (Kinv @ y), 1e-8, "NNGP posterior mean")
+    assert_close(cov, kf(Xn, Xn, 0.05) - kpx @ Kinv @ kpx.T, 1e-8, "NNGP posterior cov")
