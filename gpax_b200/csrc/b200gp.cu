@@ -1814,7 +1814,7 @@ static int dist_free(b2gp_ctx* ctx, DistState* ds) {
     NcclApi* n = nccl_api();
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&ds->Aloc, &ds->PB[0], &ds->PB[1], &ds->UB, &ds->Xrows, &ds->Zcols, &ds->yloc, &ds->red, &ds->linv, &ds->updA, &ds->updB,
+    for (DevBuf* b : {&ds->Aloc, &ds->PB[0], &ds->PB[1], &ds->UB, &ds->EB, &ds->Xrows, &ds->Zcols, &ds->yloc, &ds->red, &ds->linv, &ds->updA, &ds->updB,
                       &ds->updSA, &ds->updSB, &ds->wseg})
         free_buf(*b);
     for (auto& st : ds->steps) {
@@ -1822,9 +1822,11 @@ static int dist_free(b2gp_ctx* ctx, DistState* ds) {
         free_buf(st.g2);
         free_buf(st.bmap);
     }
-    for (cudaEvent_t e : {ds->ev_u, ds->ev_ubc, ds->ev_chunk, ds->ev_comm[0], ds->ev_comm[1], ds->ev_done})
+    for (cudaEvent_t e : {ds->ev_u, ds->ev_ubc[0], ds->ev_ubc[1], ds->ev_chunk, ds->ev_comm[0], ds->ev_comm[1], ds->ev_done, ds->ev_e,
+                          ds->ev_early[0], ds->ev_early[1], ds->ev_g2})
         if (e) cudaEventDestroy(e);
     if (ds->ms) cudaStreamDestroy(ds->ms);
+    if (ds->dq) cudaStreamDestroy(ds->dq);
     if (n->handle) {
         if (ds->rowc) n->CommDestroy(ds->rowc);
         if (ds->colc) n->CommDestroy(ds->colc);
@@ -1870,7 +1872,9 @@ extern "C" int b2gp_dist_init(b2gp_ctx* ctx, const void* id128, int rank, int nr
     NCCL_TRY(ctx, n->CommSplit(ds->world, ds->g.myrow, ds->g.mycol, &ds->rowc, nullptr));
     NCCL_TRY(ctx, n->CommSplit(ds->world, ds->g.mycol, ds->g.myrow, &ds->colc, nullptr));
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ds->ms, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&ds->ev_u, &ds->ev_ubc, &ds->ev_chunk, &ds->ev_comm[0], &ds->ev_comm[1], &ds->ev_done})
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ds->dq, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ds->ev_u, &ds->ev_ubc[0], &ds->ev_ubc[1], &ds->ev_chunk, &ds->ev_comm[0], &ds->ev_comm[1], &ds->ev_done, &ds->ev_e,
+                           &ds->ev_early[0], &ds->ev_early[1], &ds->ev_g2})
         CUDA_TRY(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     ds->ready = true;
     return B2GP_OK;
@@ -1952,6 +1956,7 @@ static int dist_build_steps(b2gp_ctx* ctx, DistState* ds, cudaStream_t st, int C
                     for (int64_t ti = b0; ti < b1; ++ti) {
                         const int64_t gi = (li0 + ti / t128) * g.pr + g.myrow;
                         if (gi < gj) continue;
+                        if (gi == k + 1 && gj == k + 1) continue;    // the next diagonal tile takes panel k on the diagonal stream (diag_factor)
                         (c == next_col ? l1 : l2).push_back(make_int2((int)ti, (int)(c * ent_per_tile + e)));
                     }
             }
@@ -1987,7 +1992,7 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     ARG_CHECK(ctx, kind >= 0 && kind <= 2);
     ARG_CHECK(ctx, Xtr && yres && Xnew && theta && mean && info);
     ARG_CHECK(ctx, N >= 1 && P >= 1 && d >= 1 && d <= GRAM_MAX_D);
-    ARG_CHECK(ctx, nb >= 128 && nb % 128 == 0 && N % nb == 0);
+    ARG_CHECK(ctx, nb >= 128 && nb <= 1024 && nb % 128 == 0 && N % nb == 0);
     ARG_CHECK(ctx, !(flags & B2GP_FLAG_DEVICE_PTRS) && !(flags & (B2GP_OUT_COV | B2GP_OUT_SAMPLE)));
     if (ctx->ozaki == 0) return set_err(ctx, B2GP_ERR_UNSUPPORTED, "b2gp_dist_posterior", "needs the int8 path (ozaki != 0)", __FILE__, __LINE__);
     const bool want_var = flags & B2GP_OUT_VAR;
@@ -2034,7 +2039,8 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     RET_IF(ensure(ctx, ds->yloc, yl.size() * 8));
     RET_IF(ensure(ctx, ctx->d_in[3], (size_t)nth * 8));
     RET_IF(ensure(ctx, ds->Aloc, (size_t)std::max<int64_t>(Lr * nb * ld, 1) * 8));
-    RET_IF(ensure(ctx, ds->UB, (size_t)nb * nb * 8));
+    RET_IF(ensure(ctx, ds->UB, (size_t)2 * nb * nb * 8));     // U of two consecutive steps
+    RET_IF(ensure(ctx, ds->EB, (size_t)2 * nb * nb * 8));     // early tiles of two consecutive steps
     RET_IF(ensure(ctx, ds->linv, (size_t)linv_bytes(nb)));
     RET_IF(ensure(ctx, ds->red, (size_t)(4 * P + 64) * 8));
     RET_IF(ensure(ctx, ds->wseg, (size_t)std::max<int64_t>(ld, 1) * 8));
@@ -2050,7 +2056,6 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     CUDA_TRY(ctx, cudaStreamSynchronize(cs));   // the host staging vectors are pageable
     const double* dth = (const double*)ctx->d_in[3].p;
     double* A = (double*)ds->Aloc.p;
-    double* UB = (double*)ds->UB.p;
     sl.oz_planes = ctx->ozaki > 0 ? ctx->ozaki : oz_auto_planes((double)N, theta[d], theta[d + 1], jitter);
 
     // ---- the local matrix, generated in place: k(rows, columns) for every local tile, then the diagonal term and y
@@ -2077,9 +2082,9 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     cudaEvent_t ev_f0 = ctx->slots[0].ev[2], ev_f1 = ctx->slots[0].ev[3];
     CUDA_TRY(ctx, cudaEventRecord(ev_f0, cs));
 
-    // optional phase profile (B2GP_DIST_PROF=1): CUDA events on both streams, summed per phase after the call
+    // optional phase profile (B2GP_DIST_PROF=1): CUDA events on the streams, summed per phase after the call
     const bool prof = getenv("B2GP_DIST_PROF") != nullptr;
-    enum { PH_SLICE, PH_G1, PH_POTRF, PH_UWAIT, PH_PANEL, PH_G2, PH_COMMWAIT, PH_UBCAST, PH_ROWBCAST, PH_ALLGATHER, PH_N };
+    enum { PH_SLICE, PH_G1, PH_POTRF, PH_UWAIT, PH_PANEL, PH_G2, PH_COMMWAIT, PH_UBCAST, PH_ROWBCAST, PH_ALLGATHER, PH_EARLY, PH_N };
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pev[PH_N];
     auto mark = [&](cudaStream_t s) -> cudaEvent_t {
         if (!prof) return nullptr;
@@ -2090,45 +2095,79 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     auto span = [&](int ph, cudaEvent_t a, cudaEvent_t b) {
         if (prof && a && b) pev[ph].emplace_back(a, b);
     };
+    cudaStream_t dq = ds->dq;                         // the diagonal tiles are factored on their own stream, one step ahead
+    double* UBs[2] = {(double*)ds->UB.p, (double*)ds->UB.p + nb * nb};
+    double* EBs[2] = {(double*)ds->EB.p, (double*)ds->EB.p + nb * nb};
+    auto diag_tile = [&](int64_t k) { return A + ((k / pr) * nb) * ld + (k / pc) * nb; };
 
-    // ---- panel pipeline pieces
-    auto panel_front_a = [&](int64_t k) -> int {   // (a), (b) of step k: diagonal tile on its owner, U on its way down the column
+    // ---- (a), (b) of step k on stream s: the owner folds in the tile (k, k-1) it received ahead of the panel
+    // (`early`), factors the diagonal tile and forms U = L_kk^{-T}; every rank of the process column joins the broadcast
+    // of U on the communication stream.  ev_ubc[k & 1] marks "U_k is here" for the panel solve.
+    auto diag_factor = [&](int64_t k, cudaStream_t s, bool early) -> int {
         const int kr = (int)(k % pr), kc = (int)(k % pc);
-        cudaEvent_t p0 = mark(cs);
-        if (mycol == kc) {
-            if (myrow == kr) {
-                double* D = A + ((k / pr) * nb) * ld + (k / pc) * nb;
-                RET_IF(potrf_rec(ctx, cs, D, ld, nb, (double*)ds->linv.p, dinfo, k * nb));
-                set_identity_kernel<<<grid_for(nb * nb), 256, 0, cs>>>(UB, nb, nb);
-                CUDA_TRY(ctx, cudaGetLastError());
-                ctx->launches++;
-                RET_IF(trsm_rec(ctx, cs, UB, nb, nb, D, ld, nb, (const double*)ds->linv.p));      // U = L_kk^{-T}
+        if (mycol != kc) return B2GP_OK;
+        double* U = UBs[k & 1];
+        if (myrow == kr) {
+            cudaEvent_t p0 = mark(s);
+            double* D = diag_tile(k);
+            if (early) {   // D -= E E^T, E = L tile (k, k-1): from the early broadcast, or in place when this rank solved it itself
+                const bool local = (pc == 1);
+                const double* E = local ? A + (g.first_row_after(k - 1, myrow) * nb) * ld + ((k - 1) / pc) * nb : EBs[(k - 1) & 1];
+                RET_IF(gemm_nt(ctx, s, nb, nb, nb, -1.0, E, local ? ld : nb, E, local ? ld : nb, 1.0, D, ld, true));
             }
-            cudaEvent_t p1 = mark(cs);
-            span(PH_POTRF, p0, p1);
-            if (pr > 1) {
-                CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, cs));
-                CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_u, 0));
-                cudaEvent_t m0 = mark(ms);
-                NCCL_TRY(ctx, nc->Broadcast(UB, UB, (size_t)(nb * nb), ncclDouble, kr, ds->colc, ms));
-                span(PH_UBCAST, m0, mark(ms));
-                CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc, ms));
-            }
+            RET_IF(potrf_rec(ctx, s, D, ld, nb, (double*)ds->linv.p, dinfo, k * nb));
+            set_identity_kernel<<<grid_for(nb * nb), 256, 0, s>>>(U, nb, nb);
+            CUDA_TRY(ctx, cudaGetLastError());
+            ctx->launches++;
+            RET_IF(trsm_rec(ctx, s, U, nb, nb, D, ld, nb, (const double*)ds->linv.p));      // U = L_kk^{-T}
+            span(PH_POTRF, p0, mark(s));
+        }
+        if (pr > 1) {
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, s));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_u, 0));
+            cudaEvent_t m0 = mark(ms);
+            NCCL_TRY(ctx, nc->Broadcast(U, U, (size_t)(nb * nb), ncclDouble, kr, ds->colc, ms));
+            span(PH_UBCAST, m0, mark(ms));
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc[k & 1], ms));
+        } else {
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc[k & 1], s));
         }
         return B2GP_OK;
     };
-    auto panel_front_b = [&](int64_t k) -> int {   // (c) .. (f) of step k: panel solve once U is here, pack, panel exchange
+    // ---- (c) .. (f) of step k on the compute stream: panel solve once U is here, the tile (k+1, k) sent ahead to the owner
+    // of the next diagonal tile (row communicator), pack, panel exchange
+    auto panel_front_b = [&](int64_t k) -> int {
         const int kc = (int)(k % pc);
         const int64_t li0 = g.first_row_after(k, myrow), rows = g.panel_rows(k, myrow), slot = g.slot_rows(k);
         double* PBk = (double*)ds->PB[k & 1].p;
+        double* rp = A + (li0 * nb) * ld + (k / pc) * nb;
         if (mycol == kc) {
             cudaEvent_t p1 = mark(cs);
-            if (pr > 1) CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc[k & 1], 0));
             cudaEvent_t p0 = mark(cs);
             span(PH_UWAIT, p1, p0);
+            if (rows > 0) RET_IF(ozaki_dispatch(ctx, cs, rows, nb, nb, 1.0, rp, ld, UBs[k & 1], nb, rp, ld, false, true, true, true));
+        }
+        if (k + 1 < T && myrow == (int)((k + 1) % pr)) {      // my process row holds tile (k+1, k) -- the first tile of its panel rows
+            if (pc > 1) {
+                if (mycol == kc) {
+                    copy2d_kernel<<<grid_for(nb * nb), 256, 0, cs>>>(EBs[k & 1], nb, rp, ld, nb, nb);
+                    CUDA_TRY(ctx, cudaGetLastError());
+                    ctx->launches++;
+                }
+                CUDA_TRY(ctx, cudaEventRecord(ds->ev_e, cs));
+                CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_e, 0));
+                cudaEvent_t m0 = mark(ms);
+                NCCL_TRY(ctx, nc->Broadcast(EBs[k & 1], EBs[k & 1], (size_t)(nb * nb), ncclDouble, kc, ds->rowc, ms));
+                span(PH_EARLY, m0, mark(ms));
+                CUDA_TRY(ctx, cudaEventRecord(ds->ev_early[k & 1], ms));
+            } else {
+                CUDA_TRY(ctx, cudaEventRecord(ds->ev_early[k & 1], cs));
+            }
+        }
+        if (mycol == kc) {
+            cudaEvent_t p0 = mark(cs);
             if (rows > 0) {
-                double* rp = A + (li0 * nb) * ld + (k / pc) * nb;
-                RET_IF(ozaki_dispatch(ctx, cs, rows, nb, nb, 1.0, rp, ld, UB, nb, rp, ld, false, true, true, true));
                 copy2d_kernel<<<grid_for(rows * nb), 256, 0, cs>>>(PBk + (int64_t)myrow * slot * nb, nb, rp, ld, rows, nb);
                 CUDA_TRY(ctx, cudaGetLastError());
                 ctx->launches++;
@@ -2148,6 +2187,19 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
         }
         CUDA_TRY(ctx, cudaEventRecord(ds->ev_comm[k & 1], ms));
         return B2GP_OK;
+    };
+    // ---- diagonal look-ahead: tile j's last update (from panel j-1) and its factorisation run on the diagonal stream as
+    // soon as the tile (j, j-1) has arrived and the compute stream has applied panels < j-1 to it (ev_g2)
+    auto diag_ahead = [&](int64_t j) -> int {
+        if (j >= T) return B2GP_OK;
+        const bool in_col = mycol == (int)(j % pc), owner = in_col && myrow == (int)(j % pr);
+        if (!in_col) return B2GP_OK;
+        if (owner) {
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_g2, cs));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(dq, ds->ev_g2, 0));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(dq, ds->ev_early[(j - 1) & 1], 0));
+        }
+        return diag_factor(j, dq, true);
     };
     OzOperand opA, opB;
     OzMode upd_mode;
@@ -2177,32 +2229,17 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
         return oz_mma_launch<7>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt);
     };
 
-    // ---- the factorisation (with the right-hand-side rows riding below)
-    // Program order of one step on the compute stream.  The owner of the next diagonal tile factors it right after g1; the
-    // other ranks of its process column have nothing to do until U arrives, so THEY run the bulk update g2 first (it
-    // overlaps the owner's latency-bound factorisation); ranks of other columns only feed the exchange.
-    auto panel_front = [&](int64_t k, int64_t upd_k) -> int {
-        const bool in_col = (mycol == (int)(k % pc)), owner = in_col && (myrow == (int)(k % pr));
-        RET_IF(panel_front_a(k));
-        const bool g2_first = upd_k >= 0 && in_col && !owner && pr > 1;
-        cudaEvent_t q3 = nullptr;
-        if (g2_first) {
-            q3 = mark(cs);
-            RET_IF(update_part(upd_k, 2));
-            span(PH_G2, q3, mark(cs));
-        }
-        RET_IF(panel_front_b(k));
-        if (upd_k >= 0 && !g2_first) {
-            q3 = mark(cs);
-            RET_IF(update_part(upd_k, 2));
-            span(PH_G2, q3, mark(cs));
-        }
-        return B2GP_OK;
-    };
-    // the persistent int8 kernels leave a few SMs to the NCCL kernels of the exchange running beside them
+    // ---- the factorisation (with the right-hand-side rows riding below).  Compute stream, step k: wait for panel k;
+    // slices; g1 (tile column k+1 without its diagonal tile, which the diagonal stream owns); panel solve / early tile /
+    // exchange of step k+1; g2; then hand tile k+2 to the diagonal stream.
+    // the persistent int8 kernels leave a few SMs to the NCCL kernels and the diagonal-tile kernels running beside them
     const int big_grid_saved = ctx->big_grid;
-    if (ds->nranks > 1 && ctx->big_grid == 0) ctx->big_grid = ctx->sm_count - 16;
-    RET_IF(panel_front(0, -1));
+    if (ctx->big_grid == 0) ctx->big_grid = ctx->sm_count - 16;
+    CUDA_TRY(ctx, cudaEventRecord(ds->ev_g2, cs));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(dq, ds->ev_g2, 0));          // the diagonal stream starts behind the Gram build
+    RET_IF(diag_factor(0, cs, false));
+    RET_IF(panel_front_b(0));
+    RET_IF(diag_ahead(1));
     for (int64_t k = 0; k < T; ++k) {
         cudaEvent_t q0 = mark(cs);
         CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_comm[k & 1], 0));
@@ -2213,14 +2250,14 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
         span(PH_SLICE, q1, q2);
         RET_IF(update_part(k, 1));
         span(PH_G1, q2, mark(cs));
-        if (k + 1 < T) {
-            RET_IF(panel_front(k + 1, k));
-        } else {
-            cudaEvent_t q3 = mark(cs);
-            RET_IF(update_part(k, 2));
-            span(PH_G2, q3, mark(cs));
-        }
+        if (k + 1 < T) RET_IF(panel_front_b(k + 1));
+        cudaEvent_t q3 = mark(cs);
+        RET_IF(update_part(k, 2));
+        span(PH_G2, q3, mark(cs));
+        RET_IF(diag_ahead(k + 2));
     }
+    CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, dq));                   // the compute stream ends behind the diagonal stream
+    CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_u, 0));
     ctx->big_grid = big_grid_saved;
     CUDA_TRY(ctx, cudaEventRecord(ev_f1, cs));
 
@@ -2236,8 +2273,8 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
             CUDA_TRY(ctx, cudaEventRecord(ds->ev_u, cs));
             CUDA_TRY(ctx, cudaStreamWaitEvent(ms, ds->ev_u, 0));
             NCCL_TRY(ctx, nc->Broadcast(wseg, wseg, (size_t)ld, ncclDouble, (int)(gy % pr), ds->colc, ms));
-            CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc, ms));
-            CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc, 0));
+            CUDA_TRY(ctx, cudaEventRecord(ds->ev_ubc[0], ms));
+            CUDA_TRY(ctx, cudaStreamWaitEvent(cs, ds->ev_ubc[0], 0));
         }
         for (int64_t li = 0; li < Lr && Lc > 0; ++li) {
             const int64_t gi = li * pr + myrow;
@@ -2268,9 +2305,10 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     CUDA_TRY(ctx, cudaEventElapsedTime(&ms_f, ev_f0, ev_f1));
     ex->last.potrf_ms = ms_f;
     if (prof) {
-        static const char* names[PH_N] = {"update slices", "g1 (next tile column)", "diag potrf + U", "wait for U broadcast", "panel solve + pack",
+        static const char* names[PH_N] = {"update slices", "g1 (next tile column)", "[diag stream] early update + potrf + U", "wait for U", "panel solve + pack",
                                           "g2 (rest of the update)", "wait for the panel exchange", "[comm stream] U broadcast",
-                                          "[comm stream] panel row broadcast", "[comm stream] panel column all-gather"};
+                                          "[comm stream] panel row broadcast", "[comm stream] panel column all-gather",
+                                          "[comm stream] early tile broadcast"};
         fprintf(stderr, "[dist prof] rank %d (%d,%d) N=%lld nb=%lld factorisation %.2f ms:", ds->rank, myrow, mycol, (long long)N, (long long)nb, ms_f);
         for (int ph = 0; ph < PH_N; ++ph) {
             double tot = 0.0;

@@ -24,9 +24,13 @@
 //   (g) trailing update of the local matrix, C -= P_rows P_cols^T: ONE int8 GEMM whose A operand is this process row's
 //       slot, whose B operand gathers the panel tiles of this process's tile columns through a row map, and whose tile
 //       list is the staircase gi >= gj of the block-cyclic lower triangle.
-// Look-ahead: (g) is split into the tile column of step k+1 (g1) and the rest (g2); the compute stream runs g1_k, then
-// (a), (c), (d) of step k+1, then g2_k, so the collectives (b), (e), (f) of step k+1 -- on their own stream -- overlap
-// the bulk of step k's update.
+// Look-ahead, two kinds.  (i) (g) is split into the tile column of step k+1 (g1) and the rest (g2); the compute stream
+// runs g1_k, then (c), (d) of step k+1, then g2_k, so the collectives (e), (f) of step k+1 -- on their own stream --
+// overlap the bulk of step k's update.  (ii) Diagonal look-ahead: the tile (k+1, k) is broadcast along its process row
+// AHEAD of the panel, right after the panel solve; the owner of diagonal tile k+1 applies it (D -= E E^T), factors the
+// tile and forms U on a third stream while the panel of step k is still being exchanged and applied -- the 0.4 ms
+// latency chain of the 128-wide leaves leaves the critical path, which becomes panel solve -> early tile -> (factor) ->
+// U broadcast -> next panel solve.
 #pragma once
 #include <dlfcn.h>
 #include <nccl.h>
@@ -123,9 +127,10 @@ struct DistState {
     int rank = 0, nranks = 1;
     BcGrid g;
     ncclComm_t world = nullptr, rowc = nullptr, colc = nullptr;
-    cudaStream_t ms = nullptr;
-    cudaEvent_t ev_u = nullptr, ev_ubc = nullptr, ev_chunk = nullptr, ev_comm[2] = {nullptr, nullptr}, ev_done = nullptr;
-    DevBuf Aloc, PB[2], UB, Xrows, Zcols, yloc, red, linv, updA, updB, updSA, updSB, wseg;
+    cudaStream_t ms = nullptr, dq = nullptr;     // communication stream, diagonal-tile stream
+    cudaEvent_t ev_u = nullptr, ev_ubc[2] = {nullptr, nullptr}, ev_chunk = nullptr, ev_comm[2] = {nullptr, nullptr}, ev_done = nullptr;
+    cudaEvent_t ev_e = nullptr, ev_early[2] = {nullptr, nullptr}, ev_g2 = nullptr;
+    DevBuf Aloc, PB[2], UB, EB, Xrows, Zcols, yloc, red, linv, updA, updB, updSA, updSB, wseg;
     std::vector<DistStep> steps;
     int64_t cache_T = -1, cache_R = -1, cache_nb = -1;
     int cache_cl = -1;
