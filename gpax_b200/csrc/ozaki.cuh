@@ -31,7 +31,9 @@
 #include "common.cuh"
 #include "gemm_tma.cuh"
 
-constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32, OZ_STAGES = 4;   // 32-byte k-blocks (one MMA K step), 4 stages in flight
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KB = 32;   // 32-byte k-blocks (one MMA K step)
+// stages in flight: as many as fit beside the epilogue's staging tile -- 5 x 36 KB with 6 planes, 4 x 42 KB with 7
+__host__ __device__ constexpr int oz_stages_for(int S) { return S <= 6 ? 5 : 4; }
 constexpr int OZ_THREADS = 192;
 constexpr int OZ_K_MAX = 16384;           // int32 accumulation bound of one launch (see above)
 constexpr int OZ_A_TILE = OZ_BM * OZ_KB;  // 4096 B
@@ -224,6 +226,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
     const int tile_first = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     constexpr int STAGE_BYTES = S * (OZ_A_TILE + OZ_B_TILE);
+    constexpr int OZ_STAGES = oz_stages_for(S);
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
@@ -597,7 +600,7 @@ static int oz_mma_launch(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, const OzOper
     a.prof = nullptr;
     if (w.prof.p) a.prof = (long long*)w.prof.p;
     a.debug = ctx->oz_debug;
-    constexpr int smem_bytes = OZ_STAGES * S * (OZ_A_TILE + OZ_B_TILE) + 128 + (128 * 17 + 128) * 8 + 1024;
+    constexpr int smem_bytes = oz_stages_for(S) * S * (OZ_A_TILE + OZ_B_TILE) + 128 + (128 * 17 + 128) * 8 + 1024;
     static PerDeviceOnce attr;
     if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));

@@ -1,5 +1,9 @@
 """
-distributed.py -- the two multi-GPU forms of the path that need a real exchange step:
+distributed.py -- ROUND-1 PROTOTYPE of the two multi-GPU forms of the path, kept as the host-side reference of the 1-D
+(block-column) layout and for its gloo CPU tests.  The product is the in-library version: gpax_b200/dist.py over
+gpax_b200/csrc/dist.cuh (2-D block-cyclic layout, NCCL row / column communicators inside libb200gp.so, no torch).
+
+The two forms that need a real exchange step:
 
   * `BlockCyclicGP`: exact-GP posterior with the N x N matrix distributed block-column-cyclically over
     the ranks (one process per GPU).  Right-looking Cholesky: the owner of block column k factors its
@@ -44,11 +48,17 @@ class GpuOps:
     def empty(self, shape):
         return self.torch.empty(shape, dtype=self.torch.float64, device=self.device)
 
+    # torch produces these buffers on ITS current stream; libb200gp consumes them on its own non-blocking streams, and
+    # nothing else orders the two: wait for torch's stream before handing a freshly written buffer to the library
+    def _ordered(self, t):
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return t
+
     def zeros(self, shape):
-        return self.torch.zeros(shape, dtype=self.torch.float64, device=self.device)
+        return self._ordered(self.torch.zeros(shape, dtype=self.torch.float64, device=self.device))
 
     def from_numpy(self, a):
-        return self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+        return self._ordered(self.torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device))
 
     def to_numpy(self, t):
         return t.detach().cpu().numpy()
