@@ -10,9 +10,11 @@ from .gp import ExactGP
 from .vigp import viGP
 from .sparse_gp import viSparseGP
 from .variants import MeasuredNoiseGP, UIGP, VarNoiseGP, vExactGP
-from . import acquisition
+from . import acquisition, mtkernels
+from .kernels import NNGPKernel
+from .mtkernels import LCMKernel, MultitaskKernel, MultivariateKernel
 from ._ffi import B200GPError, Context, default_context
 
 __version__ = "0.1.0"
-__all__ = ["ExactGP", "viGP", "viSparseGP", "MeasuredNoiseGP", "VarNoiseGP", "vExactGP", "UIGP", "acquisition", "RBFKernel", "MaternKernel", "PeriodicKernel", "get_kernel",
+__all__ = ["ExactGP", "viGP", "viSparseGP", "MeasuredNoiseGP", "VarNoiseGP", "vExactGP", "UIGP", "acquisition", "RBFKernel", "MaternKernel", "PeriodicKernel", "NNGPKernel", "MultitaskKernel", "MultivariateKernel", "LCMKernel", "mtkernels", "get_kernel",
            "kernels", "utils", "Context", "default_context", "B200GPError"]

@@ -59,6 +59,8 @@ SIGNATURES = {
     "b2gp_sync": (C.c_int, [_vp]),
     "b2gp_gram": (C.c_int, [_vp, C.c_int, _vp, C.c_int64, _vp, C.c_int64, C.c_int, _vp, C.c_double, C.c_double,
                             C.c_double, C.c_int, _vp, C.c_int64, C.c_uint]),
+    "b2gp_gram_multitask": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_int, _vp, C.c_double, C.c_double, _vp,
+                                      C.c_int, _vp, C.c_double, C.c_int, C.c_int, _vp, C.c_int64, C.c_uint]),
     "b2gp_potrf": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _ip, C.c_uint]),
     "b2gp_trsm_lower": (C.c_int, [_vp, C.c_int64, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, C.c_uint]),
     "b2gp_gemm_nt": (C.c_int, [_vp, C.c_int64, C.c_int64, C.c_int64, C.c_double, _vp, C.c_int64, _vp, C.c_int64,
@@ -252,6 +254,19 @@ class Context:
         self._check(self.lib.b2gp_gram(self.h, KIND[kind] if isinstance(kind, str) else kind, _ptr(X), n, _ptr(Z), m, d,
                                        _ptr(ell), float(scale), float(period), float(diag_add), int(bool(same_xz)),
                                        _ptr(K), m, flags))
+        return K
+
+    def gram_multitask(self, kind, X, tX, Z, tZ, lengthscale, scale, period, B, noise_task, jitter, same_xz, group=1):
+        X, Z, B = _f64(X), _f64(Z), _f64(B)
+        n, d = X.shape
+        m = Z.shape[0]
+        tX, tZ = np.ascontiguousarray(tX, dtype=np.int32), np.ascontiguousarray(tZ, dtype=np.int32)
+        ell = _f64(np.broadcast_to(np.asarray(lengthscale, dtype=np.float64).reshape(-1), (d,)))
+        nt = None if noise_task is None else _f64(noise_task)
+        K = np.empty((n, m))
+        self._check(self.lib.b2gp_gram_multitask(self.h, kind if isinstance(kind, int) else KIND[kind], _ptr(X), _ptr(tX), n, _ptr(Z), _ptr(tZ),
+                                                 m, d, _ptr(ell), float(scale), float(period), _ptr(B), B.shape[0], _ptr(nt), float(jitter),
+                                                 int(bool(same_xz)), int(group), _ptr(K), m, 0))
         return K
 
     def potrf(self, A):

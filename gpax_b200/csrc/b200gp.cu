@@ -463,6 +463,68 @@ extern "C" int b2gp_gram(b2gp_ctx* ctx, int kind, const double* X, int64_t n, co
     return B2GP_OK;
 }
 
+// Multi-task Gram matrices (gpax/kernels/mtkernels.py:19-58 index_kernel, 61-125 MultitaskKernel):
+//   K[i, j] = (k_data(x_i, z_j) + jitter [same point, same_xz]) * B[tX_i, tZ_j]  (+ noise_task[tX_i] + jitter on i == j when same_xz)
+// -- the reference calls the data kernel with noise 0 but its usual diagonal rule, so k_data carries `jitter` where the two
+// points coincide (mtkernels.py:103, 167); `group` consecutive rows are one data point (1, or the task count for the
+// Kronecker form, whose jitter therefore lands on the whole T x T diagonal block).
+// B = W W^T + diag(v) (T x T, formed by the caller: T^2 numbers).  The data kernel is the fused Gram kernel; the task factor
+// is applied in place by one elementwise pass.  MultivariateKernel's Kronecker form (mtkernels.py:128-192) is the same
+// thing on inputs repeated once per task with the task index cycling fastest (the shell does that).
+__global__ void mt_task_kernel(double* K, int64_t ld, int64_t n, int64_t m, const int* __restrict__ tX, const int* __restrict__ tZ,
+                               const double* __restrict__ B, int T, const double* __restrict__ noise_task, double jitter, int same_xz,
+                               int group) {
+    const int64_t total = n * m;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx / m, j = idx % m;
+        double kd = K[i * ld + j];
+        if (same_xz && i / group == j / group) kd += jitter;
+        double v = kd * B[(int64_t)tX[i] * T + tZ[j]];
+        if (same_xz && i == j) v += (noise_task ? noise_task[tX[i]] : 0.0) + jitter;
+        K[i * ld + j] = v;
+    }
+}
+
+extern "C" int b2gp_gram_multitask(b2gp_ctx* ctx, int kind, const double* X, const int* taskX, int64_t n, const double* Z,
+                                   const int* taskZ, int64_t m, int d, const double* lengthscale, double scale, double period,
+                                   const double* B, int T, const double* noise_task, double jitter, int same_xz, int group,
+                                   double* K, int64_t ldk, unsigned flags) {
+    if (!ctx) return B2GP_ERR_ARG;
+    ARG_CHECK(ctx, kind >= 0 && kind <= B2GP_KERNEL_NNGP_RELU);
+    ARG_CHECK(ctx, X && Z && taskX && taskZ && B && K && lengthscale);
+    ARG_CHECK(ctx, n >= 1 && m >= 1 && T >= 1 && group >= 1 && d >= 1 && d <= GRAM_MAX_D && ldk >= m);
+    ARG_CHECK(ctx, !(flags & (B2GP_FLAG_DEVICE_PTRS | B2GP_FLAG_F32)));      // host fp64 arrays (a callable-kernel building block)
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Extra* ex = extra_of(ctx);
+    cudaStream_t st = ctx->slots[0].stream;
+    CallTimer tm(ctx);
+    RET_IF(tm.begin(st));
+    double th[GRAM_MAX_D + 3];
+    for (int k = 0; k < d; ++k) th[k] = lengthscale[k];
+    th[d] = scale;
+    th[d + 1] = 0.0;
+    th[d + 2] = period;
+    RET_IF(ensure(ctx, ex->theta1, sizeof th));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ex->theta1.p, th, (d + 3) * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    const double *dX, *dZ, *dB, *dn = nullptr, *dtx, *dtz;
+    RET_IF(stage_in(ctx, st, ctx->d_in[0], X, (size_t)n * d * 8, false, &dX));
+    RET_IF(stage_in(ctx, st, ctx->d_in[1], Z, (size_t)m * d * 8, false, &dZ));
+    RET_IF(stage_in(ctx, st, ctx->d_in[2], B, (size_t)T * T * 8, false, &dB));
+    if (noise_task) RET_IF(stage_in(ctx, st, ctx->d_in[4], noise_task, (size_t)T * 8, false, &dn));
+    RET_IF(stage_in(ctx, st, ctx->d_in[5], taskX, (size_t)n * 4, false, &dtx));
+    RET_IF(stage_in(ctx, st, ctx->d_in[6], taskZ, (size_t)m * 4, false, &dtz));
+    const int64_t ld = round_up(m, 2);
+    RET_IF(ensure(ctx, ctx->d_out[0], (size_t)n * ld * 8));
+    double* dK = (double*)ctx->d_out[0].p;
+    RET_IF(launch_gram(ctx, st, kind, dX, n, dZ, m, d, (const double*)ex->theta1.p, 0.0, 0.0, 0, 0, dK, ld));
+    mt_task_kernel<<<grid_for(n * m), 256, 0, st>>>(dK, ld, n, m, (const int*)dtx, (const int*)dtz, dB, T, dn, jitter, same_xz ? 1 : 0, group);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    CUDA_TRY(ctx, cudaMemcpy2DAsync(K, (size_t)ldk * 8, dK, (size_t)ld * 8, (size_t)m * 8, (size_t)n, cudaMemcpyDeviceToHost, st));
+    return tm.end(st, nullptr);
+}
+
 // ------------------------------------------------------------------------------------------ potrf / trsm / gemm
 extern "C" int b2gp_potrf(b2gp_ctx* ctx, int64_t n, double* A, int64_t lda, int* info, unsigned flags) {
     if (!ctx) return B2GP_ERR_ARG;

@@ -116,6 +116,17 @@ int  b2gp_gram(b2gp_ctx* ctx, int kind,
                double diag_add, int same_xz,
                double* K, int64_t ldk, unsigned flags);
 
+/* Multi-task Gram matrix -- gpax/kernels/mtkernels.py:19-58 (index_kernel) and 61-125 (MultitaskKernel):
+ * K[i,j] = (k_data(x_i, z_j) + jitter if same point) * B[taskX[i], taskZ[j]], plus noise_task[taskX[i]] + jitter on i == j,
+ * both iff same_xz (the reference's shape rule).  B[T,T] = W W^T + diag(v) is formed by the caller.  Host fp64 / int32
+ * arrays.  The Kronecker form of MultivariateKernel (mtkernels.py:128-192) is this call on inputs repeated once per
+ * task with group = T (`group` consecutive rows are one data point; 1 otherwise).                                     */
+int  b2gp_gram_multitask(b2gp_ctx* ctx, int kind, const double* X, const int* taskX, int64_t n,
+                         const double* Z, const int* taskZ, int64_t m, int d,
+                         const double* lengthscale, double scale, double period,
+                         const double* B, int T, const double* noise_task, double jitter, int same_xz, int group,
+                         double* K, int64_t ldk, unsigned flags);
+
 /* Cholesky factorisation A = L L^T of the lower triangle, in place (row-major, lower); the strict
  * upper triangle is not referenced and not modified.  Stands where the reference inverts k_XX
  * (jnp.linalg.inv, gpax/models/gp.py:271) and where viSparseGP calls jax.scipy.linalg.cholesky

@@ -74,3 +74,33 @@ def measured_noise_logp(X, y, params, measured_noise, kernel="RBF", jitter=1e-6)
     L = sla.cholesky(k, lower=True)
     a = sla.solve_triangular(L, y, lower=True)
     return -0.5 * a @ a - np.log(np.diag(L)).sum() - 0.5 * len(y) * np.log(2 * np.pi)
+
+
+# ---- multi-task kernels (gpax/kernels/mtkernels.py)
+def _task_cov(params):
+    W, v = np.asarray(params["W"]), np.asarray(params["v"])
+    return W @ W.T + np.diag(v)                                                              # mtkernels.py:55-57
+
+
+def multitask_kernel(X, Z, params, noise, kernel="RBF", jitter=1e-6):
+    """mtkernels.py:89-123: k_data(x, z) * B[task(x), task(z)], per-task noise + jitter on the diagonal when shapes agree."""
+    Xd, tX, Zd, tZ = X[:, :-1], X[:, -1].astype(int), Z[:, :-1], Z[:, -1].astype(int)
+    K = go.get_kernel(kernel)(Xd, Zd, params, 0, jitter=jitter)    # noise 0, but the data kernel's own diagonal rule adds `jitter` (:103)
+    K = K * _task_cov(params)[np.ix_(tX, tZ)]
+    if X.shape == Z.shape:
+        K[np.diag_indices(len(X))] += np.asarray(noise)[tX] + jitter                         # :111-121
+    return K
+
+
+def multivariate_kernel(X, Z, params, noise, kernel="RBF", num_tasks=1, jitter=1e-6):
+    """mtkernels.py:161-190: kron(k_data, k_task) + kron(I, diag(noise + jitter))."""
+    K = np.kron(go.get_kernel(kernel)(X, Z, params, 0, jitter=jitter), _task_cov(params))
+    if X.shape == Z.shape:
+        K = K + np.kron(np.eye(len(X)), np.diag(np.asarray(noise) + jitter))
+    return K
+
+
+def lcm_kernel(X, Z, params, noise, kernel="RBF", jitter=1e-6):
+    """mtkernels.py:226-230 (shared_input_space=False): sum of multi-task kernels over the leading axis of the parameters."""
+    L = len(params["k_scale"])
+    return sum(multitask_kernel(X, Z, {k: np.asarray(v)[q] for k, v in params.items()}, noise, kernel, jitter) for q in range(L))

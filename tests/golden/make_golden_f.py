@@ -33,6 +33,8 @@ INJECT = {"eps": None}
 def _tree_index(a, i, axis):
     if axis is None or a is None:
         return a
+    if isinstance(axis, dict):
+        return {k: _tree_index(a[k], i, axis[k]) for k in a}
     if isinstance(a, dict):
         return {k: _tree_index(v, i, axis) for k, v in a.items()}
     if isinstance(a, (tuple, list)):
@@ -53,6 +55,9 @@ def vmap(f, in_axes=0, out_axes=0):
         axes = in_axes if isinstance(in_axes, (tuple, list)) else (in_axes,) * len(args)
         n = None
         for a, ax in zip(args, axes):
+            if isinstance(ax, dict):
+                n = len(next(a[k] for k in a if ax[k] is not None))
+                break
             if ax is not None and a is not None:
                 n = _tree_len(a)
                 break
@@ -114,7 +119,9 @@ def main():
     import gpax
     from gpax.acquisition import base_acq
     import gpax.kernels.kernels as rk
+    import gpax.kernels.mtkernels as rmt
     rk.vmap = vmap                      # kernels.py does `from jax import vmap`
+    rmt.vmap = vmap
     base_acq.jax.vmap = vmap
     rng = np.random.default_rng(20260925)
     out = {}
@@ -202,6 +209,30 @@ def main():
             prm = {"var_b": np.float64(0.3), "var_w": np.float64(1.7)}
             out[f"nngp_{act}_d{depth}_XZ"] = np.asarray(kfn(J(X), J(Z), prm, 0.05))
             out[f"nngp_{act}_d{depth}_XX"] = np.asarray(kfn(J(X), J(X), prm, 0.05))
+
+    # ---- multi-task kernels (mtkernels.py:61-232)
+    Tn = 3
+    W = rng.standard_normal((Tn, 2))
+    v = np.exp(rng.normal(-1, 0.3, Tn))
+    Xm = np.column_stack([rng.uniform(0, 1, (14, 2)), rng.integers(0, Tn, 14)])
+    Zm = np.column_stack([rng.uniform(0, 1, (9, 2)), rng.integers(0, Tn, 9)])
+    prm = {"k_length": J([0.4, 0.6]), "k_scale": np.float64(1.2), "W": J(W), "v": J(v)}
+    noise_t = J([0.01, 0.02, 0.03])
+    kmt = gpax.kernels.MultitaskKernel("Matern")
+    out["mt_X"], out["mt_Z"], out["mt_W"], out["mt_v"] = Xm, Zm, W, v
+    out["mt_XZ"] = np.asarray(kmt(J(Xm), J(Zm), prm, noise_t))
+    out["mt_XX"] = np.asarray(kmt(J(Xm), J(Xm), prm, noise_t))
+    # (a scalar noise becomes a length-1 array indexed by the task ids, mtkernels.py:113-115: that relies on JAX clamping
+    #  out-of-range gathers, which NumPy does not do -- not generated here)
+    kmv = gpax.kernels.MultivariateKernel("RBF", Tn)
+    out["mv_XZ"] = np.asarray(kmv(J(Xm[:, :2]), J(Zm[:, :2]), prm, noise_t))
+    out["mv_XX"] = np.asarray(kmv(J(Xm[:, :2]), J(Xm[:, :2]), prm, noise_t))
+    klcm = gpax.kernels.LCMKernel("RBF", shared_input_space=False)
+    prm2 = {"k_length": J(rng.uniform(0.3, 0.7, (2, 2))), "k_scale": J([1.1, 0.7]), "W": J(rng.standard_normal((2, Tn, 2))),
+            "v": J(np.exp(rng.normal(-1, 0.3, (2, Tn))))}
+    for k_ in ("k_length", "k_scale", "W", "v"):
+        out["lcm_" + k_] = np.asarray(prm2[k_])
+    out["lcm_XX"] = np.asarray(klcm(J(Xm), J(Xm), prm2, noise_t))
 
     # ---- MeasuredNoiseGP: the model covariance k + diag(measured_noise) (mngp.py:92-97) and the log density of y under it
     N = 30

@@ -237,3 +237,32 @@ def test_nngp_kernel_golden(gp, gf):
     kpx = kf(Xn, X, 0.0, 0.0)
     assert_close(mean, kpx @ (Kinv @ y), 1e-8, "NNGP posterior mean")
     assert_close(cov, kf(Xn, Xn, 0.05) - kpx @ Kinv @ kpx.T, 1e-8, "NNGP posterior cov")
+
+
+def test_multitask_kernels_golden(gp, gf):
+    """gpax/kernels/mtkernels.py on the GPU (b2gp_gram_multitask) against the reference's own output, and a posterior with a
+    multi-task kernel through the callable path"""
+    from gpax_b200 import mtkernels as mt
+    prm = {"k_length": np.array([0.4, 0.6]), "k_scale": 1.2, "W": gf["mt_W"], "v": gf["mt_v"]}
+    nt = np.array([0.01, 0.02, 0.03])
+    kmt = mt.MultitaskKernel("Matern")
+    np.testing.assert_allclose(kmt(gf["mt_X"], gf["mt_Z"], prm, nt), gf["mt_XZ"], rtol=1e-12)
+    np.testing.assert_allclose(kmt(gf["mt_X"], gf["mt_X"], prm, nt), gf["mt_XX"], rtol=1e-12)
+    kmv = mt.MultivariateKernel("RBF", 3)
+    np.testing.assert_allclose(kmv(gf["mt_X"][:, :2], gf["mt_Z"][:, :2], prm, nt), gf["mv_XZ"], rtol=1e-12)
+    np.testing.assert_allclose(kmv(gf["mt_X"][:, :2], gf["mt_X"][:, :2], prm, nt), gf["mv_XX"], rtol=1e-12)
+    prm2 = {k: gf["lcm_" + k] for k in ("k_length", "k_scale", "W", "v")}
+    np.testing.assert_allclose(mt.LCMKernel("RBF", shared_input_space=False)(gf["mt_X"], gf["mt_X"], prm2, nt), gf["lcm_XX"], rtol=1e-12)
+    rng = np.random.default_rng(3)
+    X = np.column_stack([rng.uniform(0, 1, (300, 1)), rng.integers(0, 3, 300)])
+    y = np.sin(6 * X[:, 0]) * (1 + 0.3 * X[:, 1]) + 0.05 * rng.standard_normal(300)
+    Xn = np.column_stack([np.linspace(0, 1, 40), np.full(40, 1)])
+    m = gp.ExactGP(2, kmt)
+    m.X_train, m.y_train = X, y
+    params = {"k_length": np.array([0.3]), "k_scale": 1.0, "W": gf["mt_W"], "v": gf["mt_v"], "noise": np.array([0.01, 0.02, 0.03])}
+    mean, cov = m.get_mvn_posterior(Xn, params)
+    from oracle import variants_oracle as vo
+    kf = lambda A, B_, n_: vo.multitask_kernel(A, B_, params, n_, "Matern")     # noqa: E731
+    Kinv = np.linalg.inv(kf(X, X, params["noise"]))
+    kpx = vo.multitask_kernel(Xn, X, params, params["noise"], "Matern", jitter=0.0)
+    assert_close(mean, kpx @ (Kinv @ y), 1e-8, "multi-task posterior mean")

@@ -70,3 +70,15 @@ def test_measured_noise_logp(gf):
     prm = {"k_length": np.array([0.4]), "k_scale": 1.2}
     v = vo.measured_noise_logp(gf["mn_Xtr"], gf["mn_ytr"], prm, gf["mn_noise"])
     np.testing.assert_allclose(v, gf["mn_logp"], rtol=1e-12)
+
+
+def test_multitask_kernels(gf):
+    """oracle/variants_oracle.multitask_kernel / multivariate_kernel / lcm_kernel vs the reference's mtkernels.py"""
+    prm = {"k_length": np.array([0.4, 0.6]), "k_scale": 1.2, "W": gf["mt_W"], "v": gf["mt_v"]}
+    nt = np.array([0.01, 0.02, 0.03])
+    np.testing.assert_allclose(vo.multitask_kernel(gf["mt_X"], gf["mt_Z"], prm, nt, "Matern"), gf["mt_XZ"], rtol=1e-13)
+    np.testing.assert_allclose(vo.multitask_kernel(gf["mt_X"], gf["mt_X"], prm, nt, "Matern"), gf["mt_XX"], rtol=1e-13)
+    np.testing.assert_allclose(vo.multivariate_kernel(gf["mt_X"][:, :2], gf["mt_Z"][:, :2], prm, nt, "RBF", 3), gf["mv_XZ"], rtol=1e-13)
+    np.testing.assert_allclose(vo.multivariate_kernel(gf["mt_X"][:, :2], gf["mt_X"][:, :2], prm, nt, "RBF", 3), gf["mv_XX"], rtol=1e-13)
+    prm2 = {k: gf["lcm_" + k] for k in ("k_length", "k_scale", "W", "v")}
+    np.testing.assert_allclose(vo.lcm_kernel(gf["mt_X"], gf["mt_X"], prm2, nt, "RBF"), gf["lcm_XX"], rtol=1e-13)
