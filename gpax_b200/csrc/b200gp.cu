@@ -2371,7 +2371,9 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
                                           "g2 (rest of the update)", "wait for the panel exchange", "[comm stream] U broadcast",
                                           "[comm stream] panel row broadcast", "[comm stream] panel column all-gather",
                                           "[comm stream] early tile broadcast"};
-        fprintf(stderr, "[dist prof] rank %d (%d,%d) N=%lld nb=%lld factorisation %.2f ms:", ds->rank, myrow, mycol, (long long)N, (long long)nb, ms_f);
+        char line[2048];
+        int off = snprintf(line, sizeof line, "[dist prof] rank %d (%d,%d) N=%lld nb=%lld factorisation %.2f ms:", ds->rank, myrow, mycol,
+                           (long long)N, (long long)nb, ms_f);
         for (int ph = 0; ph < PH_N; ++ph) {
             double tot = 0.0;
             for (auto& pe : pev[ph]) {
@@ -2379,9 +2381,9 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
                 cudaEventElapsedTime(&f, pe.first, pe.second);
                 tot += f;
             }
-            fprintf(stderr, " %s %.2f;", names[ph], tot);
+            if (off < (int)sizeof line) off += snprintf(line + off, sizeof line - off, " %s %.2f;", names[ph], tot);
         }
-        fprintf(stderr, "\n");
+        fprintf(stderr, "%s\n", line);     // one write per rank: the ranks share a terminal
     }
     const double n = (double)N, p = (double)P;
     ex->last.flops = n * n * n / 3.0 + n * n * (p + 1.0) + 4.0 * n * p;
