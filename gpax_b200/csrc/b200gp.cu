@@ -227,7 +227,7 @@ extern "C" int b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value) {
         return B2GP_OK;
     }
     if (strcmp(key, "oz_cluster") == 0) {
-        ARG_CHECK(ctx, value == 1 || value == 2 || value == 4);
+        ARG_CHECK(ctx, value == 1 || value == 2);
         ctx->oz_cluster = (int)value;
         return B2GP_OK;
     }
@@ -2070,7 +2070,7 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
     g.R = ceil_div(P + 1, nb);
     const int pr = g.pr, pc = g.pc, myrow = g.myrow, mycol = g.mycol;
     const int64_t T = g.T, Lr = g.lr(myrow), Lc = g.lc(mycol), ld = Lc * nb;
-    const int CL = (ctx->oz_cluster >= 2) ? 2 : 1;     // the staircase lists are built for CTA pairs (128-row granularity)
+    const int CL = (ctx->oz_cluster == 2) ? 2 : 1;
     const int nth = d + 3;
     CallTimer tm(ctx);
     RET_IF(tm.begin(cs));
@@ -2287,8 +2287,8 @@ extern "C" int b2gp_dist_posterior(b2gp_ctx* ctx, int kind, const double* Xtr, i
         const int64_t rows = g.panel_rows(k, myrow), cols = (Lc - lj0) * nb;
         double* C = A + (li0 * nb) * ld + lj0 * nb;
         const int2* list = (const int2*)(part == 1 ? s.g1.p : s.g2.p);
-        if (sl.oz_planes == 6) return oz_mma_launch<6>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt, CL);
-        return oz_mma_launch<7>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt, CL);
+        if (sl.oz_planes == 6) return oz_mma_launch<6>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt);
+        return oz_mma_launch<7>(ctx, cs, sl.oz, opA, opB, rows, cols, nb, -1.0, C, ld, false, upd_mode, list, cnt);
     };
 
     // ---- the factorisation (with the right-hand-side rows riding below).  Compute stream, step k: wait for panel k;

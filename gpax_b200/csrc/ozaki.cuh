@@ -220,20 +220,10 @@ __device__ __forceinline__ void oz_tile_of(int x, int lower_only, int tiles_n, i
 // digit planes, so each CTA fetches half of them and TMA multicasts every box into both shared memories (the L2 -> SM
 // operand traffic, which is what bounds this kernel, drops from 48 to 32 KB per CTA and k-block).  A stage may be
 // refilled only when BOTH CTAs have consumed it: the `empty` barriers count two commits, one multicast from each.
-// CL = 4: a 2 x 2 arrangement -- CTA (rr, cc) = cluster rank 2 rr + cc works on row block 2 I + rr, column tile 2 J + cc of
-// list entry (I, J).  The A planes of a row block are shared by the two CTAs of that cluster row (each fetches half and
-// multicasts to both), the B planes of a column tile by the two CTAs of that cluster column: 18 instead of 24 KB of L2 -> SM
-// reads per CTA and k-block with 6 planes.  A stage of CTA X is written by X, its row peer and its column peer, so its
-// `empty` barrier counts three commits and every CTA multicasts its commit to those three.
 template <int S, int CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzArgs p) {
-    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
-    constexpr int RW = CL == 4 ? 2 : 1, CW = CL == 4 ? 2 : CL;     // row blocks / column tiles per list entry
-    const uint32_t rr = CL == 4 ? (crank >> 1) : 0u, cc = CL == 4 ? (crank & 1u) : crank;
-    const uint16_t amask = CL == 4 ? (uint16_t)(3u << (2u * rr)) : (uint16_t)3;               // CTAs sharing my A planes
-    const uint16_t bmask = (uint16_t)((1u << cc) | (1u << (2u + cc)));                          // CTAs sharing my B planes (CL = 4)
-    const uint16_t cmask = CL == 4 ? (uint16_t)((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u))) : (uint16_t)3;
+    const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u;
     const int tile_first = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
     constexpr int STAGE_BYTES = S * (OZ_A_TILE + OZ_B_TILE);
     constexpr int OZ_STAGES = oz_stages_for(S);
@@ -250,7 +240,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, CL == 4 ? 3 : CL);
+            mbar_init(empty0 + 8 * s, CL);
         }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
@@ -262,7 +252,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();   // the peers' barriers exist before anything is multicast at them
+    if (CL == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_gen;
 
@@ -272,8 +262,8 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
             uint32_t it = 0;
             for (int tile = tile_first; tile < p.num_tiles; tile += tile_step) {
                 const int2 tt = p.tile_list[tile];
-                const int row0 = (RW * tt.x + (int)rr) * OZ_BM, col0 = (CW * tt.y + (int)cc) * OZ_BN;
-                const int kbn = oz_kb_count(p, CW, tt.y);
+                const int row0 = tt.x * OZ_BM, col0 = (CL * tt.y + (int)crank) * OZ_BN;
+                const int kbn = oz_kb_count(p, CL, tt.y);
                 for (int kb = 0; kb < kbn; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -283,12 +273,9 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                     for (int q = 0; q < S; ++q) {
                         if (CL == 1)
                             tma_load_2d(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s);
-                        else if ((q < (S + 1) / 2) == (cc == 0))
-                            tma_load_2d_mc(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s, amask);
-                        if (CL != 4)
-                            tma_load_2d(st + S * OZ_A_TILE + q * OZ_B_TILE, &mapB, kb * OZ_KB, q * p.rowsB_pad + col0, full0 + 8 * s);
-                        else if ((q < (S + 1) / 2) == (rr == 0))
-                            tma_load_2d_mc(st + S * OZ_A_TILE + q * OZ_B_TILE, &mapB, kb * OZ_KB, q * p.rowsB_pad + col0, full0 + 8 * s, bmask);
+                        else if ((q < (S + 1) / 2) == (crank == 0))
+                            tma_load_2d_mc(st + q * OZ_A_TILE, &mapA, kb * OZ_KB, q * p.rowsA_pad + row0, full0 + 8 * s, (uint16_t)3);
+                        tma_load_2d(st + S * OZ_A_TILE + q * OZ_B_TILE, &mapB, kb * OZ_KB, q * p.rowsB_pad + col0, full0 + 8 * s);
                     }
                 }
             }
@@ -304,7 +291,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                 mbar_wait(acc_empty, (tcount & 1u) ^ 1u);   // epilogue of the previous tile has drained TMEM
                 m_empty += clock64() - e0;
                 tc_fence_after();
-                const int kbn = oz_kb_count(p, CW, p.tile_list[tile].y);
+                const int kbn = oz_kb_count(p, CL, p.tile_list[tile].y);
                 for (int kb = 0; kb < kbn; ++kb, ++it) {
                     const uint32_t s = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     const long long f0 = p.prof ? clock64() : 0;
@@ -330,8 +317,8 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
                             tc_mma_i8(tmem + 64u * (pp + 4), ad, oz_smem_desc(st + S * OZ_A_TILE + 4 * OZ_B_TILE),
                                       IDESC_BASE | ((uint32_t)((nq - 4) * OZ_BN >> 3) << 17), acc);
                     }
-                    if (CL > 1)
-                        tc_commit_mc(empty0 + 8 * s, cmask);
+                    if (CL == 2)
+                        tc_commit_mc(empty0 + 8 * s, (uint16_t)3);
                     else
                         tc_commit(empty0 + 8 * s);
                 }
@@ -350,7 +337,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
         long long c_wait = 0, c_ld = 0, c_upd = 0;
         for (int tile = tile_first; tile < p.num_tiles; tile += tile_step, ++tcount) {
             const int2 tt = p.tile_list[tile];
-            const int ti = RW * tt.x + (int)rr, tj = CW * tt.y + (int)cc;
+            const int ti = tt.x, tj = CL * tt.y + (int)crank;
             const int row = ti * OZ_BM + 32 * quarter + lane;
             const int col0 = tj * OZ_BN;
             // coalesced mapping of the C update: 16 consecutive threads cover the 128 bytes of one row of a 16-column chunk
@@ -440,7 +427,7 @@ oz_mma_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();   // no commit of mine may still be on its way to a peer that has exited
+    if (CL == 2) cluster_sync_all();   // no commit of mine may still be on its way to a peer that has exited
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
@@ -546,9 +533,7 @@ static int oz_default_list(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int tiles_
     // being equally long, in k-lockstep: if those tiles form a compact block of (row block, column block) pairs, each
     // operand block is fetched from HBM once per round and served to the other tiles from L2.  Bands of G row blocks,
     // column-major inside a band: a round covers ~G x (sm_count/G) tiles = G + sm_count/G distinct operand blocks.
-    const int CW = CL == 4 ? 2 : CL, RW = CL == 4 ? 2 : 1;
-    const int pairs_n = (tiles_n + CW - 1) / CW;   // list entries per row block: column tiles (CL = 1) or pairs of them
-    const int rows_e = (tiles_m + RW - 1) / RW;    // row entries: row blocks, or pairs of them (CL = 4)
+    const int pairs_n = (tiles_n + CL - 1) / CL;   // list entries per row block: column tiles (CL = 1) or pairs of them
     OzTileList* tl = nullptr;
     for (auto& l : w.lists)
         if (l.tm == tiles_m && l.tn == tiles_n && l.lower == (lower_only ? 1 : 0) && l.cl == CL) tl = &l;
@@ -557,16 +542,15 @@ static int oz_default_list(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int tiles_
         tl = &w.lists[w.next_list];
         w.next_list = (w.next_list + 1) % OZ_LISTS;
         tl->host.clear();
-        // lower: row block ti owns column tiles 0 .. 2 ti + 1 = pairs 0 .. ti; a PAIR of row blocks (CL = 4) owns pairs 0 .. 2 I + 1
-        auto last_of = [&](int e) { return CL == 4 ? 2 * e + 1 : (CL == 2 ? e : 2 * e + 1); };
-        const int G = CL == 4 ? 4 : 8;
-        for (int b0 = 0; b0 < rows_e; b0 += G) {
-            const int b1 = b0 + G < rows_e ? b0 + G : rows_e;
-            const int last = lower_only ? last_of(b1 - 1) : pairs_n - 1;
+        const int G = 8;
+        for (int b0 = 0; b0 < tiles_m; b0 += G) {
+            const int b1 = b0 + G < tiles_m ? b0 + G : tiles_m;
+            // lower: row block ti owns column tiles 0 .. 2 ti + 1, i.e. pairs 0 .. ti
+            const int last = lower_only ? (CL == 2 ? b1 - 1 : 2 * (b1 - 1) + 1) : pairs_n - 1;
             const int jmax = last < pairs_n - 1 ? last : pairs_n - 1;
             for (int tj = 0; tj <= jmax; ++tj)
                 for (int ti = b0; ti < b1; ++ti)
-                    if (!lower_only || tj <= last_of(ti)) tl->host.push_back(make_int2(ti, tj));
+                    if (!lower_only || tj <= (CL == 2 ? ti : 2 * ti + 1)) tl->host.push_back(make_int2(ti, tj));
         }
         tl->tm = tiles_m;
         tl->tn = tiles_n;
@@ -586,8 +570,7 @@ static int oz_default_list(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, int tiles_
 // the default tile order: the distributed factorisation passes the staircase of a block-cyclic trailing matrix.
 template <int S>
 static int oz_mma_launch(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, const OzOperand& oa, const OzOperand& ob, int64_t m, int64_t n,
-                         int64_t k, double alpha, double* C, int64_t ldc, bool lower_only, OzMode mode, const int2* list, int64_t count,
-                         int list_cl = 0) {
+                         int64_t k, double alpha, double* C, int64_t ldc, bool lower_only, OzMode mode, const int2* list, int64_t count) {
     const int64_t kpad = round_up(k, OZ_KB);
     CUtensorMap mapA, mapB;
     if (!make_tmap_u8(&mapA, oa.planes, (int64_t)S * oa.rows_pad, kpad, OZ_BM) || !make_tmap_u8(&mapB, ob.planes, (int64_t)S * ob.rows_pad, kpad, OZ_BN))
@@ -608,8 +591,7 @@ static int oz_mma_launch(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, const OzOper
     a.ktri = mode.ktri ? 1 : 0;
     a.tiles_m = (int)ceil_div(m, OZ_BM);
     a.tiles_n = (int)ceil_div(n, OZ_BN);
-    // caller-built lists (the block-cyclic staircases) fix their own cluster shape; default lists follow the option
-    const int CL = list ? list_cl : (ctx->oz_cluster == 4 ? 4 : (ctx->oz_cluster == 2 ? 2 : 1));
+    const int CL = (ctx->oz_cluster == 2) ? 2 : 1;
     if (!list) RET_IF(oz_default_list(ctx, st, w, a.tiles_m, a.tiles_n, lower_only, CL, &list, &count));
     if (count <= 0) return B2GP_OK;
     const int64_t tiles = count;
@@ -623,28 +605,24 @@ static int oz_mma_launch(b2gp_ctx* ctx, cudaStream_t st, OzWork& w, const OzOper
     if (attr.need(ctx->device)) {
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(oz_mma_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr.done(ctx->device);
     }
     const int nsm = persist_sms(ctx);
-    if (CL >= 2) {
-        const int ncl = nsm / CL;
+    if (CL == 2) {
+        const int ncl = nsm / 2;
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(CL * (tiles < ncl ? tiles : ncl)));
+        cfg.gridDim = dim3((unsigned)(2 * (tiles < ncl ? tiles : ncl)));
         cfg.blockDim = dim3(OZ_THREADS);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = (unsigned)CL;
+        at[0].val.clusterDim.x = 2;
         at[0].val.clusterDim.y = 1;
         at[0].val.clusterDim.z = 1;
         cfg.attrs = at;
         cfg.numAttrs = 1;
-        if (CL == 4)
-            CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, oz_mma_kernel<S, 4>, mapA, mapB, a));
-        else
-            CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, oz_mma_kernel<S, 2>, mapA, mapB, a));
+        CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, oz_mma_kernel<S, 2>, mapA, mapB, a));
     } else {
         const int grid = (int)(tiles < nsm ? tiles : nsm);
         oz_mma_kernel<S, 1><<<grid, OZ_THREADS, smem_bytes, st>>>(mapA, mapB, a);

@@ -56,7 +56,7 @@ if mode == "small":
         run(S, 512, 512, 200, True, True)
         run(S, 1024, 1024, 1024, True, True)
 elif mode == "prof":          # run with B2GP_OZ_PROF=1: issuer / epilogue cycle counters per tile; cluster 2 and 1
-    for cl in (4, 2, 1):
+    for cl in (2, 1):
         ctx.set_option("oz_cluster", cl)
         print(f"--- oz_cluster = {cl}", flush=True)
         for S in (6, 7):
