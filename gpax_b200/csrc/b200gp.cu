@@ -1054,7 +1054,7 @@ static int sparse_partial_dev(b2gp_ctx* ctx, Slot& sl, int kind, const double* d
     double* W = (double*)sl.cov.p;
     // Kuu = kernel(Xu, Xu, params, **kwargs): noise defaults to 0, so the diagonal gets jitter only (sparse_gp.py:193)
     RET_IF(launch_gram(ctx, st, kind, dXu, M, dXu, M, d, dth, 0.0, jitter, 1, 1, Luu, ldM));
-    RET_IF(potrf_rec(ctx, st, Luu, ldM, M, LinvU, dinfo, 0));                                   // sparse_gp.py:194
+    RET_IF(potrf_auto(ctx, st, Luu, ldM, M, 0, LinvU, dinfo));                                  // sparse_gp.py:194
     // W^T = K_fu Luu^{-T}  (W = Luu^{-1} Kuf, sparse_gp.py:195-197), one training point per row
     RET_IF(launch_gram(ctx, st, kind, dXtr, N, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wt, ldM));
     RET_IF(trsm_rec(ctx, st, Wt, ldM, N, Luu, ldM, M, LinvU));   // tall right-hand sides: int8 panel GEMMs (potrf.cuh)
@@ -1064,8 +1064,11 @@ static int sparse_partial_dev(b2gp_ctx* ctx, Slot& sl, int kind, const double* d
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
     }
-    // W D^{-1} W^T with D = noise * 1  (sparse_gp.py:198-199); 1/noise applied after the sum
-    RET_IF(gemm_nt(ctx, st, M, M, N, 1.0 / noise_h, W, ldN, W, ldN, 0.0, Kpart, ldk, true));
+    // W D^{-1} W^T with D = noise * 1  (sparse_gp.py:198-199).  Accumulated onto a zeroed matrix (beta = 1) so that the
+    // product -- M^2 N flops, the bulk of the sparse posterior -- qualifies for the int8 tcgen05 path (k = N is split into
+    // launches of <= 16384 by the dispatcher)
+    CUDA_TRY(ctx, cudaMemsetAsync(Kpart, 0, (size_t)M * ldk * 8, st));
+    RET_IF(gemm_nt(ctx, st, M, M, N, 1.0 / noise_h, W, ldN, W, ldN, 1.0, Kpart, ldk, true));
     // W D^{-1} y  (sparse_gp.py:203-204)
     rowdot2_kernel<<<(unsigned)M, RD_THREADS, 0, st>>>(W, ldN, N, dy, 1.0 / noise_h, cpart, nullptr);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -1088,7 +1091,7 @@ static int sparse_finish_dev(b2gp_ctx* ctx, Slot& sl, int kind, const double* dX
     add_diag_kernel<<<grid_for(M), 256, 0, st>>>(Kmat, ldk, M, 1.0);                            // sparse_gp.py:200
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
-    RET_IF(potrf_rec(ctx, st, Kmat, ldk, M, LinvK, dinfo + 1, 0));                              // sparse_gp.py:201
+    RET_IF(potrf_auto(ctx, st, Kmat, ldk, M, 0, LinvK, dinfo + 1));                             // sparse_gp.py:201
     // Ws^T = K_su Luu^{-T}  (sparse_gp.py:206-207)
     RET_IF(launch_gram(ctx, st, kind, dXnew, P, dXu, M, d, dth, 0.0, 0.0, 0, 0, Wst, ldM));
     RET_IF(trsm_rec(ctx, st, Wst, ldM, P, Luu, ldM, M, LinvU));
