@@ -6,7 +6,8 @@ The reference hands `ExactGP.model` (gpax/models/gp.py:137-164) to NumPyro: NUTS
 Here the model's log joint is evaluated directly: the likelihood term and its gradient come from the GPU
 (b2gp_mll: Cholesky + solves + fused gradient reduction), the priors are the LogNormal(0,1) defaults of
 gp.py:222-247 (or gpax_b200.priors objects), and the samplers / optimiser are small host-side NumPy loops.
-Custom `kernel_prior` / `noise_prior` *functions* are NumPyro programs and cannot be interpreted here.
+Custom `kernel_prior` / `noise_prior` / `mean_fn_prior` *programs* are run on the host through gpax_b200.priors'
+`sample` / `plate` primitives (ProgramLogJoint); a program written against NumPyro itself cannot be interpreted here.
 """
 import math
 
@@ -17,16 +18,16 @@ from .utils import seed_from_key
 
 
 class LogJoint:
-    """log p(y, theta) over the unconstrained vector u, with gradient; theta = (k_length[d], k_scale, noise[, period])."""
+    """log p(y, theta) over the unconstrained vector u, with gradient; theta = (k_length[d], k_scale, noise[, period]).
+    Default priors and `*_prior_dist` objects only; `make_log_joint` picks ProgramLogJoint when the model carries prior
+    programs (kernel_prior / noise_prior / mean_fn_prior)."""
 
     def __init__(self, model, jitter=1e-6):
         if model._fused is None:
             raise NotImplementedError("fit() needs kernel 'RBF', 'Matern' or 'Periodic'")
-        if model.kernel_prior is not None or model.noise_prior is not None:
-            raise NotImplementedError("kernel_prior / noise_prior are NumPyro programs; use lengthscale_prior_dist / "
-                                      "noise_prior_dist with gpax_b200.priors objects")
-        if model.mean_fn is not None and model.mean_fn_prior is not None:
-            raise NotImplementedError("fit() with a probabilistic mean function is not implemented")
+        if model.kernel_prior is not None or model.noise_prior is not None or \
+                (model.mean_fn is not None and model.mean_fn_prior is not None):
+            raise NotImplementedError("prior programs go through ProgramLogJoint (inference.make_log_joint)")
         self.m, self.jitter = model, float(jitter)
         X, y = model._train_arrays()
         self.X, self.d = X, X.shape[1]
@@ -91,6 +92,165 @@ class LogJoint:
         return out
 
 
+class ProgramLogJoint:
+    """The log joint of ExactGP.model (gp.py:137-164) when some of its priors are *programs*: `kernel_prior()` returning
+    the kernel-parameter dict (gp.py:141-142), the deprecated `noise_prior()` (gp.py:146-147), `mean_fn_prior()` feeding a
+    parametric mean function (gp.py:151-154).  The programs are written against gpax_b200.priors' `sample` / `plate`
+    (the reference's run under NumPyro).  The model program is re-run on the host for every evaluation:
+
+      u  --transform per site-->  site values  --programs-->  theta[d+3], mean vector m[N]
+      value = log N(y - m; 0, K_theta) [GPU: b2gp_mll]  +  sum_sites log p(site)  (+ log |d site / du|)
+
+    Gradient.  The GPU returns d value / d log(theta) and alpha = K^-1 (y - m) = d value / d m.  The programs are plain
+    Python (no tracer to differentiate them), so the Jacobians d theta / du and d m / du are taken by central differences
+    of the host program -- 2 dim runs of a function of a handful of scalars and one [N]-vector, exact to ~1e-10 relative;
+    the N^3 part is never differenced.  Site log-densities are differentiated analytically; when a program makes one
+    site's distribution depend on another site's value (a hierarchical prior), the prior term's gradient is differenced
+    too."""
+
+    FD_STEP = 1e-5
+
+    def __init__(self, model, jitter=1e-6, lik=None):
+        if model._fused is None:
+            raise NotImplementedError("fit() needs kernel 'RBF', 'Matern' or 'Periodic'")
+        self.m, self.jitter = model, float(jitter)
+        X, y = model._train_arrays()
+        self.X, self.d, self.y0 = X, X.shape[1], y
+        self.kind = model._fused
+        self.has_mean_params = model.mean_fn is not None and model.mean_fn_prior is not None
+        self.fixed_mean = None
+        if model.mean_fn is not None and not self.has_mean_params:
+            self.fixed_mean = np.asarray(model.mean_fn(X), dtype=np.float64).squeeze()
+        self._lik_fn = lik
+        _, sites, _ = P.run_program(self._model_program)
+        self.sites = list(sites.values())
+        self.dim = sum(s.size for s in self.sites)
+        self.n_evals = 0
+        # does any site's distribution depend on the values of the others?  (two runs at different values)
+        vals = {s.name: np.asarray(s.prior.transform(np.full(s.shape, 0.37))) for s in self.sites}
+        _, sites2, _ = P.run_program(self._model_program, vals)
+        self.hierarchical = any(vars(sites[k].prior) != vars(sites2[k].prior) for k in sites)
+
+    # the host side of gp.py:137-154 (everything except the likelihood statement)
+    def _model_program(self):
+        m = self.m
+        if m.kernel_prior is not None:
+            kp = m.kernel_prior()
+        else:                                                              # gp.py:229-247
+            lp = m.lengthscale_prior_dist or P.LogNormal(0.0, 1.0)
+            with P.plate("ard", self.d):
+                length = P.sample("k_length", lp)
+            kp = {"k_length": length, "k_scale": P.sample("k_scale", P.LogNormal(0.0, 1.0))}
+            if self.kind == "Periodic":
+                kp["period"] = P.sample("period", P.LogNormal(0.0, 1.0))
+        if m.noise_prior is not None:
+            noise = m.noise_prior()
+        else:                                                              # gp.py:222-227
+            noise = P.sample("noise", m.noise_prior_dist or P.LogNormal(0.0, 1.0))
+        mp = m.mean_fn_prior() if self.has_mean_params else None
+        return kp, noise, mp
+
+    def _run(self, u):
+        """u -> (theta[d+3], mean vector or None, sites with values)"""
+        vals, o = {}, 0
+        for s in self.sites:
+            vals[s.name] = np.asarray(s.prior.transform(u[o:o + s.size])).reshape(s.shape)
+            o += s.size
+        (kp, noise, mp), sites, _ = P.run_program(self._model_program, vals)
+        th = np.ones(self.d + 3)
+        th[:self.d] = np.broadcast_to(np.asarray(kp["k_length"], dtype=np.float64).reshape(-1), (self.d,)) \
+            if np.size(kp["k_length"]) in (1, self.d) else np.nan
+        th[self.d] = float(np.asarray(kp["k_scale"]).reshape(-1)[0])
+        th[self.d + 1] = float(np.asarray(noise).reshape(-1)[0])
+        if self.kind == "Periodic":
+            if kp.get("period") is None:
+                raise ValueError("the Periodic kernel needs 'period' in the dict kernel_prior returns")
+            th[self.d + 2] = float(np.asarray(kp["period"]).reshape(-1)[0])
+        mean = None
+        if self.has_mean_params:
+            mean = np.asarray(self.m.mean_fn(self.X, mp), dtype=np.float64).squeeze()
+        elif self.fixed_mean is not None:
+            mean = self.fixed_mean
+        return th, mean, sites
+
+    def init_u(self):
+        """init_to_median (gp.py:208)"""
+        return np.concatenate([np.full(s.size, float(s.prior.inverse(s.prior.median()))) for s in self.sites])
+
+    def _log_prior(self, u, sites, jacobian, want_grad=True):
+        val, grad, o = 0.0, np.zeros(self.dim), 0
+        for s0 in self.sites:
+            pr = sites[s0.name].prior
+            uu = u[o:o + s0.size]
+            t = np.asarray(pr.transform(uu), dtype=np.float64)
+            val += float(np.sum(pr.log_prob(t)))
+            if want_grad:
+                grad[o:o + s0.size] = np.asarray(pr.dlog_prob(t)) * np.asarray(pr.dtheta_du(uu))
+            if jacobian:
+                val += float(np.sum(pr.log_abs_jac(uu)))
+                if want_grad:
+                    grad[o:o + s0.size] += np.asarray(pr.dlog_abs_jac(uu))
+            o += s0.size
+        return val, grad
+
+    def _lik(self, th, yres):
+        """log p(y | theta, m) with d/dlog(theta) and alpha = K^-1 (y - m)"""
+        if self._lik_fn is not None:
+            return self._lik_fn(th, yres)
+        val, g, alpha, info = self.m.ctx.mll(self.kind, self.X, yres, th, self.jitter, want_grad=True,
+                                             want_alpha=self.has_mean_params)
+        return val, g, alpha, info
+
+    def __call__(self, u, jacobian):
+        u = np.asarray(u, dtype=np.float64)
+        th, mean, sites = self._run(u)
+        self.n_evals += 1
+        if not (np.all(np.isfinite(th)) and np.all(th[:self.d + 2] > 0)):
+            return -np.inf, np.zeros(self.dim)
+        yres = self.y0 if mean is None else self.y0 - mean
+        val, g, alpha, info = self._lik(th, yres)
+        if info != 0 or not np.isfinite(val):
+            return -np.inf, np.zeros(self.dim)
+        # site densities: analytic gradient, unless the programs are hierarchical (then differenced with the rest below)
+        lp, grad = self._log_prior(u, sites, jacobian, want_grad=not self.hierarchical)
+        # chain rule through the host programs by central differences
+        h = self.FD_STEP
+        dval_dth = g / th                                   # g is d/dlog(theta); unused entries of theta carry g = 0
+        if self.has_mean_params and alpha is None:
+            raise NotImplementedError("this likelihood does not return d value / d mean: no probabilistic mean function")
+        for k in range(self.dim):
+            e = np.zeros(self.dim)
+            e[k] = h
+            thp, mp_, sp = self._run(u + e)
+            thm, mm_, sm_ = self._run(u - e)
+            grad[k] += float(np.dot(dval_dth, (thp - thm) / (2 * h)))
+            if self.has_mean_params:
+                grad[k] += float(np.dot(alpha, (mp_ - mm_) / (2 * h)))
+            if self.hierarchical:
+                lpp, _ = self._log_prior(u + e, sp, jacobian, want_grad=False)
+                lpm, _ = self._log_prior(u - e, sm_, jacobian, want_grad=False)
+                grad[k] += (lpp - lpm) / (2 * h)
+        return val + lp, grad
+
+    def to_dict(self, U):
+        """rows of unconstrained vectors -> dict of constrained site values, shapes as the program sampled them"""
+        U = np.atleast_2d(U)
+        out = {s.name: np.empty((U.shape[0],) + s.shape) for s in self.sites}
+        for r, u in enumerate(U):
+            o = 0
+            for s in self.sites:
+                out[s.name][r] = np.asarray(s.prior.transform(u[o:o + s.size])).reshape(s.shape)
+                o += s.size
+        return out
+
+
+def make_log_joint(model, jitter=1e-6):
+    if model.kernel_prior is not None or model.noise_prior is not None or \
+            (model.mean_fn is not None and model.mean_fn_prior is not None):
+        return ProgramLogJoint(model, jitter)
+    return LogJoint(model, jitter)
+
+
 # ---------------------------------------------------------------------------------------------- SVI
 class SVIState:
     def __init__(self, losses, guide, loc, scale):
@@ -100,7 +260,7 @@ class SVIState:
 def fit_vi_gp(model, rng_key, num_steps, step_size, progress_bar, **kwargs):
     """vigp.py:108-120: Adam(step_size, b1=0.5), AutoDelta (MAP in the constrained space, no Jacobian) or AutoNormal
     (mean-field normal over u, init scale 0.1, one reparameterised draw per step).  Returns (state, median dict)."""
-    lj = LogJoint(model, kwargs.get("jitter", 1e-6))
+    lj = make_log_joint(model, kwargs.get("jitter", 1e-6))
     rng = seed_from_key(rng_key)
     normal = model.guide_type == "normal"
     loc = lj.init_u()
@@ -148,10 +308,33 @@ class SparseLogJoint(LogJoint):
         return val, g, info
 
 
+def _sparse_program_log_joint(model, Xu0, jitter):
+    """ProgramLogJoint over the VFE bound; carries `Xu` / `grad_Xu` like SparseLogJoint.  (The bound's derivative w.r.t.
+    the mean vector is not computed on the device, so a probabilistic mean function is refused.)"""
+    if model.mean_fn is not None and model.mean_fn_prior is not None:
+        raise NotImplementedError("viSparseGP.fit with a probabilistic mean function is not implemented")
+    lj = ProgramLogJoint(model, jitter, lik=None)
+    lj.Xu = np.array(Xu0, dtype=np.float64, copy=True)
+    if lj.Xu.ndim == 1:
+        lj.Xu = lj.Xu[:, None]
+    lj.grad_Xu = np.zeros_like(lj.Xu)
+
+    def lik(th, yres):
+        val, g, gx, info = model.ctx.sparse_elbo(lj.kind, lj.Xu, lj.X, yres, th, lj.jitter)
+        lj.grad_Xu = gx
+        return val, g, None, info
+    lj._lik_fn = lik
+    return lj
+
+
 def fit_sparse_gp(model, rng_key, Xu0, num_steps, step_size, progress_bar, **kwargs):
     """sparse_gp.py:116-171: SVI with Adam(b1=0.5) over the hyper-parameters (delta or normal guide, as viGP) and over
     the inducing inputs Xu (a plain parameter, no prior).  Returns (state, dict with the guide median and 'Xu')."""
-    lj = SparseLogJoint(model, Xu0, kwargs.get("jitter", 1e-6))
+    if model.kernel_prior is not None or model.noise_prior is not None or \
+            (model.mean_fn is not None and model.mean_fn_prior is not None):
+        lj = _sparse_program_log_joint(model, Xu0, kwargs.get("jitter", 1e-6))
+    else:
+        lj = SparseLogJoint(model, Xu0, kwargs.get("jitter", 1e-6))
     rng = seed_from_key(rng_key)
     normal = model.guide_type == "normal"
     nu = lj.dim
@@ -288,7 +471,7 @@ def _nuts_draw(lj, u0, lp0, g0, eps, rng, minv, max_depth=10):
 
 def fit_exact_gp(model, rng_key, num_warmup, num_samples, num_chains, progress_bar, **kwargs):
     """gp.py:207-218."""
-    return run_nuts(LogJoint(model, kwargs.get("jitter", 1e-6)), rng_key, num_warmup, num_samples, num_chains, progress_bar)
+    return run_nuts(make_log_joint(model, kwargs.get("jitter", 1e-6)), rng_key, num_warmup, num_samples, num_chains, progress_bar)
 
 
 def run_nuts(lj, rng_key, num_warmup, num_samples, num_chains, progress_bar):

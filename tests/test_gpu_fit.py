@@ -206,3 +206,93 @@ def test_visparsegp_fit_then_predict():
     assert np.abs(mean - np.sin(2 * Xt)).max() < 0.25 and (var > 0).all()
     mean2, cov2 = m.get_mvn_posterior(Xt, m.get_samples(), noiseless=True)
     np.testing.assert_allclose(mean2, mean, rtol=1e-9, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------- prior programs
+def _mean_fn(x, params):                          # tests/test_gp.py:25-26
+    return params["a"] * x ** params["b"]
+
+
+def _mean_fn_priors():                            # tests/test_gp.py:29-32, numpyro -> gpax_b200.priors
+    from gpax_b200 import priors as numpyro
+    a = numpyro.sample("a", numpyro.distributions.LogNormal(0, 1))
+    b = numpyro.sample("b", numpyro.distributions.Normal(3, 1))
+    return {"a": a, "b": b}
+
+
+def _kernel_custom_prior():                       # tests/test_gp.py:35-38
+    from gpax_b200 import priors as numpyro
+    length = numpyro.sample("k_length", numpyro.distributions.Uniform(0, 1))
+    scale = numpyro.sample("k_scale", numpyro.distributions.LogNormal(0, 1))
+    return {"k_length": length, "k_scale": scale}
+
+
+def _dummy_data():                                # tests/test_gp.py:15-22, seeded
+    rng = np.random.default_rng(0)
+    X = np.linspace(1, 2, 8) + 0.1 * rng.standard_normal(8)
+    return X, 10 * X ** 2
+
+
+def test_program_log_joint_gradient_through_the_gpu():
+    """the log joint of gp.py:137-164 with kernel_prior and mean_fn_prior programs: GPU likelihood + alpha, host chain
+    rule; checked against central differences of its own value and against the NumPy likelihood"""
+    import gpax_b200
+    from gpax_b200.inference import make_log_joint, ProgramLogJoint
+    X, y = _dummy_data()
+    with pytest.warns(UserWarning):
+        m = gpax_b200.ExactGP(1, "Matern", mean_fn=_mean_fn, mean_fn_prior=_mean_fn_priors, kernel_prior=_kernel_custom_prior)
+    m.X_train, m.y_train = m._set_data(X, y)
+    lj = make_log_joint(m)
+    assert isinstance(lj, ProgramLogJoint) and lj.dim == 5
+    u = np.array([0.4, 0.3, -1.2, 2.2, 2.05])
+    val, g = lj(u, True)
+    h, fd = 1e-5, np.zeros(5)
+    for k in range(5):
+        e = np.zeros(5)
+        e[k] = h
+        fd[k] = (lj(u + e, True)[0] - lj(u - e, True)[0]) / (2 * h)
+    np.testing.assert_allclose(g, fd, rtol=1e-5, atol=1e-6)
+    th, mean, _ = lj._run(u)
+    from gpax_b200 import priors as P
+    want = mll_ref("Matern", X[:, None], y - mean, th, 1e-6)
+    want += float(P.Uniform(0, 1).log_prob(th[0])) + float(P.LogNormal().log_prob(th[1])) + float(P.LogNormal().log_prob(th[2]))
+    want += float(P.LogNormal().log_prob(np.exp(2.2))) + float(P.Normal(3, 1).log_prob(2.05))
+    s = 1 / (1 + np.exp(-0.4))
+    want += np.log(s * (1 - s)) + 0.3 - 1.2 + 2.2
+    assert abs(val - want) < 1e-8 * max(1.0, abs(want))
+
+
+@pytest.mark.parametrize("kernel", ["RBF", "Matern"])
+def test_fit_with_custom_kernel_priors(kernel):
+    """tests/test_gp.py:129-136"""
+    import gpax_b200
+    X, y = _dummy_data()
+    with pytest.warns(UserWarning):
+        m = gpax_b200.ExactGP(1, kernel, kernel_prior=_kernel_custom_prior)
+    m.fit(0, X, y, num_warmup=50, num_samples=50, progress_bar=False, print_summary=False)
+    s = m.get_samples()
+    assert m.mcmc is not None and s["k_length"].shape == (50,) and ((s["k_length"] > 0) & (s["k_length"] < 1)).all()
+
+
+def test_fit_predict_with_prob_mean_fn():
+    """tests/test_gp.py:294-301, 317-330"""
+    import gpax_b200
+    X, y = _dummy_data()
+    m = gpax_b200.ExactGP(1, "RBF", mean_fn=_mean_fn, mean_fn_prior=_mean_fn_priors)
+    m.fit(0, X, y, num_warmup=100, num_samples=100, progress_bar=False, print_summary=False)
+    s = m.get_samples()
+    assert set(s) == {"k_length", "k_scale", "noise", "a", "b"} and s["a"].shape == (100,)
+    y_pred, y_sampled = m.predict(1, X)
+    assert y_pred.shape == X.shape and y_sampled.shape == (100, 1, X.shape[0])
+    assert np.abs(y_pred - y).max() < 0.15 * np.abs(y).max()
+
+
+def test_vigp_fit_with_prob_mean_fn():
+    """tests/test_vigp.py: SVI with a probabilistic mean function (delta guide median carries the mean parameters)"""
+    import gpax_b200
+    X, y = _dummy_data()
+    m = gpax_b200.viGP(1, "RBF", mean_fn=_mean_fn, mean_fn_prior=_mean_fn_priors)
+    m.fit(0, X, y, num_steps=200, step_size=0.05, progress_bar=False, print_summary=False)
+    assert {"a", "b"} <= set(m.kernel_params)
+    mean, var = m.predict(0, X)
+    assert mean.shape == X.shape and (var > 0).all() and m.svi.losses[-10:].mean() < m.svi.losses[:10].mean()
