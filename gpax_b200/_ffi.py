@@ -184,6 +184,7 @@ class Context:
                               "(gpax_b200 has no CPU fallback)")
         self.h = h
         self.device = device
+        self._pinned = []          # pinned host blocks handed out by pinned(): released with the context
         if streams is not None:
             self.set_option("streams", streams)
 
@@ -194,7 +195,11 @@ class Context:
             raise B200GPError(f"libb200gp error {rc}: {msg.decode() if msg else ''}")
 
     def close(self):
+        """destroy the context; pinned arrays obtained from pinned() must not be used afterwards"""
         if getattr(self, "h", None) is not None:
+            for p in getattr(self, "_pinned", []):
+                self.lib.b2gp_host_free(self.h, p)
+            self._pinned = []
             self.lib.b2gp_ctx_destroy(self.h)
             self.h = None
 
@@ -229,10 +234,11 @@ class Context:
         return DeviceArray(self, host.nbytes, host.shape).upload(host)
 
     def pinned(self, shape, dtype=np.float64):
-        """NumPy array over pinned (page-locked) host memory."""
+        """NumPy array over pinned (page-locked) host memory; the block lives until close()"""
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
         p = C.c_void_p()
         self._check(self.lib.b2gp_host_alloc(self.h, n, C.byref(p)))
+        self._pinned.append(C.c_void_p(p.value))
         buf = (C.c_char * n).from_address(p.value)
         arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
         return arr

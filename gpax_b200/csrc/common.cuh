@@ -12,7 +12,7 @@
 
 #include "../../include/b200gp.h"
 
-#define B2GP_MAX_STREAMS 8
+#define B2GP_MAX_STREAMS 16
 #define B2GP_LEAF 128  // diagonal-block size of the factorisation (one CTA, shared memory)
 
 struct DevBuf {

@@ -552,12 +552,14 @@ static int launch_trsm_strip(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t 
 static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* rows, int64_t ldr, int64_t r, const double* L,
                                 int64_t ldl, int64_t n, const double* Linv128);
 
+// `panel_route` = false inside panel_solve_all_rows itself: forming U = I L^{-T} must not recurse into the panel route
+// (its scratch, Slot::panelU, is the U being formed).
 static int trsm_rec(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl,
-                    int64_t n, const double* Linv) {
+                    int64_t n, const double* Linv, bool panel_route = true) {
     if (m <= 0 || n <= 0) return B2GP_OK;
     // many right-hand sides against a factor block of at most `panel` columns: the explicit inverse of the block and ONE
     // int8 tcgen05 GEMM over all rows (see potrf_tall) instead of m/32 strips at a fraction of the DMMA rate
-    if (n > B2GP_LEAF && n <= ctx->panel && m >= 1024 && ctx->ozaki != 0) {
+    if (panel_route && n > B2GP_LEAF && n <= ctx->panel && m >= 1024 && ctx->ozaki != 0) {
         Slot* sl = slot_of(ctx, st);
         if (sl) return panel_solve_all_rows(ctx, st, *sl, B, ldb, m, L, ldl, n, Linv);
     }
@@ -567,9 +569,9 @@ static int trsm_rec(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int6
     }
     if (n <= ctx->trsm_strip) return launch_trsm_strip(ctx, st, B, ldb, m, L, ldl, n, Linv);
     const int64_t n1 = split_point(n), n2 = n - n1;
-    RET_IF(trsm_rec(ctx, st, B, ldb, m, L, ldl, n1, Linv));
+    RET_IF(trsm_rec(ctx, st, B, ldb, m, L, ldl, n1, Linv, panel_route));
     RET_IF(gemm_nt(ctx, st, m, n2, n1, -1.0, B, ldb, L + n1 * ldl, ldl, 1.0, B + n1, ldb, false));
-    return trsm_rec(ctx, st, B + n1, ldb, m, L + n1 * ldl + n1, ldl, n2, Linv + (n1 / B2GP_LEAF) * 128 * 128);
+    return trsm_rec(ctx, st, B + n1, ldb, m, L + n1 * ldl + n1, ldl, n2, Linv + (n1 / B2GP_LEAF) * 128 * 128, panel_route);
 }
 
 static int potrf_rec(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int64_t n, double* Linv, int* info,
@@ -609,7 +611,7 @@ static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double
     set_identity_kernel<<<grid_for(n * n), 256, 0, st>>>(U, ldu, n);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
-    RET_IF(trsm_rec(ctx, st, U, ldu, n, L, ldl, n, Linv128));          // U = I L^{-T}
+    RET_IF(trsm_rec(ctx, st, U, ldu, n, L, ldl, n, Linv128, false));   // U = I L^{-T}
     // rows <- rows L^{-T} = rows (L^{-1})^T: NT GEMM whose B operand L^{-1} is U read transposed
     return ozaki_dispatch(ctx, st, r, n, n, 1.0, rows, ldr, U, ldu, rows, ldr, false, true, true, true);
 }

@@ -90,7 +90,7 @@ int  b2gp_version(void);
 int  b2gp_ctx_create(int device, b2gp_ctx** out);
 int  b2gp_ctx_destroy(b2gp_ctx* ctx);
 const char* b2gp_last_error(const b2gp_ctx* ctx);
-/* options: "streams" (draws in flight, 1..8, default 2); "ozaki" (0: fp64 DMMA only, 6 / 7: int8 tcgen05 base-256 digit
+/* options: "streams" (draws in flight, 1..16, default 2); "ozaki" (0: fp64 DMMA only, 6 / 7: int8 tcgen05 base-256 digit
  * planes, -1 (default): 6 or 7 chosen per call from a bound on cond(K)); the full table is in INTEGRATION.md */
 int  b2gp_set_option(b2gp_ctx* ctx, const char* key, int64_t value);
 int  b2gp_device_info(b2gp_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* mem_bytes);

@@ -2,7 +2,7 @@
 # usage: tools/bench_variants.sh tag "opt1" "opt2 opt3" ...   (each arg = space separated key=value list, "" for defaults)
 tag=$1; shift
 for o in "$@"; do
-  args=""; for kv in $o; do if [[ $kv == streams=* ]]; then args="$args --streams ${kv#streams=}"; else args="$args --opt $kv"; fi; done
+  args=""; for kv in $o; do if [[ $kv == streams=* ]]; then args="$args --streams ${kv#streams=}"; elif [[ $kv == draws=* ]]; then args="$args --draws ${kv#draws=}"; else args="$args --opt $kv"; fi; done
   name=$(echo "$o" | tr ' =' '__'); [ -z "$name" ] && name=default
   python bench.py --steps 4 --warmup 3 --no-cpu-baseline $args > gpurun_out/${tag}_$name.json 2> gpurun_out/${tag}_$name.err
   python - <<PY
