@@ -49,7 +49,7 @@ def c2():
                "noise": np.exp(r2.normal(np.log(0.1), 0.1, S))}
     theta = np.concatenate([samples["k_length"], samples["k_scale"][:, None], samples["noise"][:, None], np.ones((S, 1))], 1)
     ctx = gpax_b200.default_context()
-    ctx.set_option("streams", 4)
+    ctx.set_option("streams", 8)
     ctx.posterior("Matern", X, y, Xn, theta[:4], want=("mean", "var"))
     t0 = time.perf_counter()
     out = ctx.posterior("Matern", X, y, Xn, theta, want=("mean", "var"), timing=True)
