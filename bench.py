@@ -450,6 +450,22 @@ def main():
     h2d = X.nbytes + y.nbytes + Xn.nbytes + theta.nbytes
     d2h = hmean.nbytes + hvar.nbytes + info.nbytes
 
+    # ---- one posterior alone (S = 1, host buffers): the latency a viGP.predict / get_mvn_posterior caller sees, with the
+    # library's own phase clock (CUDA events inside the call).  Not part of `value`; rank 0 of the N=1 run only.
+    single = None
+    if rank == 0 and world == 1:
+        lat = []
+        for _ in range(4):
+            ctx.set_option("drop_factor_cache", 1)
+            t0 = time.perf_counter()
+            o1 = ctx.posterior(w["kernel"], X, y, Xn, theta[:1], jitter=w["jitter"], want=("mean", "var"), timing=True)
+            lat.append(((time.perf_counter() - t0) * 1e3, o1["timing"]))
+        lat.sort(key=lambda r: r[0])
+        ms1, t1_ = lat[len(lat) // 2 - 1]
+        single = {"ms": ms1, "posteriors_per_s": 1e3 / ms1, "launches": int(t1_["launches"]),
+                  "phases_ms": {k_: round(float(v_), 3) for k_, v_ in t1_.items() if k_.endswith("_ms")},
+                  "note": "S=1, one stream: the chain of 32 diagonal blocks is exposed here and hidden in `value` by 8 draws in flight"}
+
     for a in (dX, dy, dXn, dth, dmean, dvar):
         a.free()
 
@@ -546,6 +562,8 @@ def main():
                           "frac": dom["dmma"]["fp64_equiv_tflops"] / peak64, "ms_per_launch": dom["dmma"]["ms"],
                           "kernel": "gemm_tma_kernel<3,2> (DMMA.8x8x4, TMA + mbarrier) + 64x64 tail launch", "peak_source": peak_src},
     }
+    if single is not None:
+        line["single_posterior"] = single
     line.update(exchange_workloads(line))
     if not args.no_cpu_baseline and world == 1:      # a reported baseline of the N=1 line only
         line["cpu_baseline"] = cpu_baseline()
