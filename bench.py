@@ -464,7 +464,7 @@ def main():
         ms1, t1_ = lat[len(lat) // 2 - 1]
         single = {"ms": ms1, "posteriors_per_s": 1e3 / ms1, "launches": int(t1_["launches"]),
                   "phases_ms": {k_: round(float(v_), 3) for k_, v_ in t1_.items() if k_.endswith("_ms")},
-                  "note": "S=1, one stream: the chain of 32 diagonal blocks is exposed here and hidden in `value` by 8 draws in flight"}
+                  "note": "S=1, one stream: the fp64 chain of the diagonal blocks is exposed here and hidden in `value` by 8 draws in flight"}
 
     for a in (dX, dy, dXn, dth, dmean, dvar):
         a.free()

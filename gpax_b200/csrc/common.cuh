@@ -61,7 +61,7 @@ struct b2gp_ctx {
     int oz_min_tiles = 148;  // smallest 128x64-tile count handed to the int8 path
     int trsm_strip = 256;  // widest factor solved by the one-launch strip kernel (0: recurse down to the 128 leaves)
     int oz_cluster = 2;  // 2: CTA pairs share the A digit planes by TMA multicast; 1: independent CTAs
-    int panel = 512;       // diagonal-block width of the tall-panel factorisation (potrf_tall); 0: recursive potrf_rec / trsm_rec only
+    int panel = 1024;      // diagonal-block width of the tall-panel factorisation (potrf_tall); 0: recursive potrf_rec / trsm_rec only
     int tall_min = 2048;   // smallest N factored by potrf_tall
     int oz_debug = 0;  // see OzArgs::debug (0 in production)
     // 0: fp64 DMMA only; 6 / 7: large rank-k updates through the int8 tcgen05 path with that many base-256 digit planes
