@@ -62,7 +62,9 @@ struct Extra {  // ctx-private state that is not part of the struct the kernels'
         std::vector<double> theta;
         std::vector<char> X;   // raw bytes of the caller's training inputs (fp64 or fp32)
         int info = 0;
+        int64_t U_nb = 0;      // > 0: `Ukeep` holds the explicit inverses of the factor's U_nb-wide diagonal blocks (potrf_tall)
     } fcache;
+    DevBuf Ukeep;
     int64_t cache_hits = 0;
     DistState* dist = nullptr;   // multi-GPU state (dist.cuh), created by b2gp_dist_init
 };
@@ -189,6 +191,7 @@ extern "C" int b2gp_ctx_destroy(b2gp_ctx* ctx) {
         for (int i = 0; i < B2GP_MAX_STREAMS; ++i) cudaEventDestroy(ex->slot_done[i]);
         cudaEventDestroy(ex->inputs_ready);
         free_buf(ex->theta1);
+        free_buf(ex->Ukeep);
         for (auto& b : ex->eb) free_buf(b);
         for (auto& b : ex->f32_in) free_buf(b);
         for (auto& b : ex->f32_out) free_buf(b);
@@ -770,6 +773,9 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
         if (reuse) ex->cache_hits++;
     }
     ex->fcache.valid = false;
+    // a cacheable call that factors by the tall-panel scheme also keeps the diagonal blocks' explicit inverses
+    const bool keepU = cacheable && !reuse && use_tall(ctx, N);
+    if (keepU) RET_IF(ensure(ctx, ex->Ukeep, (size_t)ceil_div(N, (int64_t)ctx->panel) * ctx->panel * ctx->panel * 8));
 
     // One draw's whole pipeline, queued on its slot's stream.  Returns a B2GP_* code.
     auto enqueue_draw = [&](int64_t s) -> int {
@@ -808,7 +814,7 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
             if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[1], st));
             // factor instead of jnp.linalg.inv (gp.py:271); with the tall-panel scheme also [V^T; w^T] = [k_pX; y^T] L^{-T}
             if (fused_solve)
-                RET_IF(potrf_tall(ctx, st, sl, A, ldA, N, P + 1, Linv, inf, 0));
+                RET_IF(potrf_tall(ctx, st, sl, A, ldA, N, P + 1, Linv, inf, 0, keepU ? (double*)ex->Ukeep.p : nullptr));
             else
                 RET_IF(potrf_rec(ctx, st, A, ldA, N, Linv, inf, 0));
         } else {
@@ -819,7 +825,12 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
         if (!fused_solve) RET_IF(rhs_rows());
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[3], st));
         // [V^T; w^T] = [k_pX; y^T] L^{-T}
-        if (!fused_solve) RET_IF(trsm_rec(ctx, st, Vt, ldV, P + 1, A, ldA, N, Linv));
+        if (!fused_solve) {
+            if (reuse && ex->fcache.U_nb > 0 && ex->fcache.U_nb == ctx->panel && ctx->ozaki != 0)
+                RET_IF(trsm_tall(ctx, st, Vt, ldV, P + 1, A, ldA, N, (const double*)ex->Ukeep.p, ex->fcache.U_nb));
+            else
+                RET_IF(trsm_rec(ctx, st, Vt, ldV, P + 1, A, ldA, N, Linv));
+        }
         if (timing) CUDA_TRY(ctx, cudaEventRecord(sev[s].e[4], st));
         // mean / var
         double* mean_s = want_mean ? dmean + s * P : (double*)sl.misc.p;
@@ -923,6 +934,7 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
             fc.theta.assign(theta, theta + nth);
             fc.X.assign((const char*)Xtr, (const char*)Xtr + (size_t)N * d * (f32 ? 4 : 8));
             fc.info = hinfo[0];
+            fc.U_nb = keepU ? ctx->panel : 0;
         }
         fc.valid = true;
     }

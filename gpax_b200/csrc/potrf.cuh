@@ -550,7 +550,7 @@ static int launch_trsm_strip(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t 
 // B (m x n, one right-hand side per row) <- B L^{-T}; L is n x n lower at `L`, its inverted diagonal
 // blocks at `Linv` (block b0 first).
 static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* rows, int64_t ldr, int64_t r, const double* L,
-                                int64_t ldl, int64_t n, const double* Linv128);
+                                int64_t ldl, int64_t n, const double* Linv128, double* Ukeep = nullptr);
 
 // `panel_route` = false inside panel_solve_all_rows itself: forming U = I L^{-T} must not recurse into the panel route
 // (its scratch, Slot::panelU, is the U being formed).
@@ -603,11 +603,13 @@ static int potrf_rec(b2gp_ctx* ctx, cudaStream_t st, double* A, int64_t lda, int
 // (N^2 panel flops, 1.4e11 at N = 16384 against 1.5e12 for the factorisation), and every GEMM is as tall as the matrix.
 static inline bool use_tall(const b2gp_ctx* ctx, int64_t n) { return ctx->ozaki != 0 && ctx->panel >= 128 && n >= ctx->tall_min; }
 
+// `Ukeep` (n x round_up(n, 8) doubles, caller's storage) receives U instead of the slot's scratch: the factor cache keeps
+// the explicit inverses of the diagonal blocks so that later solves against the same factor (trsm_tall) need not redo them.
 static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* rows, int64_t ldr, int64_t r, const double* L,
-                                int64_t ldl, int64_t n, const double* Linv128) {
+                                int64_t ldl, int64_t n, const double* Linv128, double* Ukeep) {
     const int64_t ldu = round_up(n, 8);
-    RET_IF(ensure(ctx, sl.panelU, (size_t)n * ldu * 8));
-    double* U = (double*)sl.panelU.p;
+    if (!Ukeep) RET_IF(ensure(ctx, sl.panelU, (size_t)n * ldu * 8));
+    double* U = Ukeep ? Ukeep : (double*)sl.panelU.p;
     set_identity_kernel<<<grid_for(n * n), 256, 0, st>>>(U, ldu, n);
     CUDA_TRY(ctx, cudaGetLastError());
     ctx->launches++;
@@ -616,21 +618,39 @@ static int panel_solve_all_rows(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double
     return ozaki_dispatch(ctx, st, r, n, n, 1.0, rows, ldr, U, ldu, rows, ldr, false, true, true, true);
 }
 
+// `Ukeep`: optional storage of panel x panel doubles per diagonal block (block b at Ukeep + b panel^2) that receives the
+// blocks' explicit inverses U_b = L_bb^{-T} (leading dimension round_up(block size, 8)); see trsm_tall.
 static int potrf_tall(b2gp_ctx* ctx, cudaStream_t st, Slot& sl, double* A, int64_t lda, int64_t n, int64_t r, double* Linv128,
-                      int* info, int64_t index_base) {
+                      int* info, int64_t index_base, double* Ukeep = nullptr) {
     if (n <= 0) return B2GP_OK;
     const int64_t NB = ctx->panel;
     if (n <= NB) {
         RET_IF(potrf_rec(ctx, st, A, lda, n, Linv128, info, index_base));
-        if (r > 0) RET_IF(panel_solve_all_rows(ctx, st, sl, A + n * lda, lda, r, A, lda, n, Linv128));
+        double* Ub = Ukeep ? Ukeep + (index_base / NB) * NB * NB : nullptr;
+        if (r > 0) RET_IF(panel_solve_all_rows(ctx, st, sl, A + n * lda, lda, r, A, lda, n, Linv128, Ub));
         return B2GP_OK;
     }
     const int64_t nblk = ceil_div(n, NB);
     const int64_t n1 = (nblk + 1) / 2 * NB, n2 = n - n1;
-    RET_IF(potrf_tall(ctx, st, sl, A, lda, n1, n2 + r, Linv128, info, index_base));
+    RET_IF(potrf_tall(ctx, st, sl, A, lda, n1, n2 + r, Linv128, info, index_base, Ukeep));
     double* Pn = A + n1 * lda;   // [A21; E1]: n2 + r rows, n1 columns, solved
     RET_IF(gemm_nt(ctx, st, n2 + r, n2, n1, -1.0, Pn, lda, Pn, lda, 1.0, Pn + n1, lda, true));
-    return potrf_tall(ctx, st, sl, Pn + n1, lda, n2, r, Linv128 + (n1 / B2GP_LEAF) * 128 * 128, info, index_base + n1);
+    return potrf_tall(ctx, st, sl, Pn + n1, lda, n2, r, Linv128 + (n1 / B2GP_LEAF) * 128 * 128, info, index_base + n1, Ukeep);
+}
+
+// B (m rows, one right-hand side per row) <- B L^{-T} against a factor whose diagonal blocks' explicit inverses were kept
+// by potrf_tall (`Ukeep`, block width NB): per block column  B_b <- B_b U_b  (int8 GEMM, k = NB, k-triangular) and
+// B[:, after b] -= B_b L[after b, b]^T.  2 N / NB machine-wide GEMMs instead of trsm_rec's 2 N / 128 strip and thin-GEMM
+// launches -- the solve of every posterior call that reuses a cached factor (chunk loops, repeated predictions).
+static int trsm_tall(b2gp_ctx* ctx, cudaStream_t st, double* B, int64_t ldb, int64_t m, const double* L, int64_t ldl, int64_t N,
+                     const double* Ukeep, int64_t NB) {
+    for (int64_t c0 = 0; c0 < N; c0 += NB) {
+        const int64_t n = N - c0 < NB ? N - c0 : NB, rest = N - c0 - n;
+        const double* U = Ukeep + (c0 / NB) * NB * NB;
+        RET_IF(ozaki_dispatch(ctx, st, m, n, n, 1.0, B + c0, ldb, U, round_up(n, 8), B + c0, ldb, false, true, true, true));
+        if (rest > 0) RET_IF(gemm_nt(ctx, st, m, rest, n, -1.0, B + c0, ldb, L + (c0 + n) * ldl + c0, ldl, 1.0, B + c0 + n, ldb, false));
+    }
+    return B2GP_OK;
 }
 
 // factorisation (+ solve of r appended rows) by whichever scheme fits the size

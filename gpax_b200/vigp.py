@@ -55,11 +55,21 @@ class viGP(ExactGP):
 
     def predict_in_batches(self, rng_key, X_new, batch_size: int = 100, samples=None, predict_fn=None,
                            noiseless: bool = False, device=None, **kwargs: float) -> Tuple[np.ndarray, np.ndarray]:
-        """vigp.py:129-151."""
-        predict_fn = lambda xi: self.predict(rng_key, xi, samples, noiseless, **kwargs)   # noqa: E731
+        """vigp.py:129-151.  The reference chunks X_new to bound the P x P covariance it forms per chunk and re-inverts
+        k_XX for every chunk.  Here (mean, var) of a test point do not depend on which other points share its chunk, the
+        factor is kept between chunks, and no P x P matrix exists, so chunks smaller than INTERNAL_BATCH rows are merged
+        before they go to the device: same outputs, the triangular solve runs on machine-filling panels instead of
+        `batch_size`-row slivers (default 100).  A user `predict_fn` keeps the caller's chunking."""
+        if predict_fn is None:
+            batch_size = max(int(batch_size), self.INTERNAL_BATCH)
+            if np.asarray(X_new).shape[0] <= batch_size:        # split_in_batches would drop a short single chunk
+                return self.predict(rng_key, X_new, samples, noiseless, **kwargs)
+            predict_fn = lambda xi: self.predict(rng_key, xi, samples, noiseless, **kwargs)   # noqa: E731
         y_pred, y_var = self._predict_in_batches(rng_key, X_new, batch_size, 0, samples, predict_fn=predict_fn,
                                                  noiseless=noiseless, device=device, **kwargs)
         return np.concatenate(y_pred, 0), np.concatenate(y_var, 0)
+
+    INTERNAL_BATCH = 8192
 
     def _print_summary(self) -> None:
         print("\nInferred GP parameters")

@@ -131,10 +131,17 @@ def test_predict_in_batches_reuses_factor():
     m.ctx.set_option("drop_factor_cache", 1)
     h0 = fn(m.ctx.h)
     mean, var = m.predict(0, Xt, params)
+    m.INTERNAL_BATCH = 1                          # the caller's chunks as they are: 11 library calls, 11 cache hits
     mb, vb = m.predict_in_batches(0, Xt, 10, params)
     assert fn(m.ctx.h) - h0 >= 10
     np.testing.assert_allclose(mb, mean, rtol=1e-12, atol=1e-13)
     np.testing.assert_allclose(vb, var, rtol=1e-11, atol=1e-13)
+    del m.INTERNAL_BATCH                          # default: chunks below 8192 rows are merged -> one call, same outputs
+    h1 = fn(m.ctx.h)
+    mc, vc = m.predict_in_batches(0, Xt, 10, params)
+    assert fn(m.ctx.h) - h1 == 1
+    np.testing.assert_array_equal(mc, mean)
+    np.testing.assert_array_equal(vc, var)
     # a different training set must not reuse the factor
     m.X_train = X + 0.01
     mean2, _ = m.predict(0, Xt, params)
