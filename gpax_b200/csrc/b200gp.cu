@@ -732,7 +732,18 @@ static int posterior_impl(b2gp_ctx* ctx, int kind, const double* Xtr, int64_t xt
     const bool need_cov = want_cov || want_samp;
     for (int q = 0; q < nslots; ++q) {
         Slot& sl = ctx->slots[q];
-        RET_IF(ensure(ctx, sl.A, (size_t)(N + P + 1) * ldA * 8));
+        const size_t needA = (size_t)(N + P + 1) * ldA * 8;
+        if (q == 0 && ex->fcache.valid && ex->fcache.N == N && sl.A.p && sl.A.cap < needA) {
+            // slot 0's matrix holds the cached factor and this call brings more test points than the one that made it:
+            // grow the buffer AROUND the factor (a plain ensure() would free it and the reuse below would read garbage)
+            DevBuf grown;
+            RET_IF(ensure(ctx, grown, needA));
+            CUDA_TRY(ctx, cudaMemcpyAsync(grown.p, sl.A.p, (size_t)N * ldA * 8, cudaMemcpyDeviceToDevice, st0));
+            CUDA_TRY(ctx, cudaStreamSynchronize(st0));
+            free_buf(sl.A);
+            sl.A = grown;
+        }
+        RET_IF(ensure(ctx, sl.A, needA));
         RET_IF(ensure(ctx, sl.Linv, (size_t)linv_bytes(N)));
         if (need_cov) RET_IF(ensure(ctx, sl.cov, (size_t)P * ldC * 8));
         if (want_samp) RET_IF(ensure(ctx, sl.LinvC, (size_t)linv_bytes(P)));

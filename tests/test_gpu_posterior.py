@@ -332,3 +332,32 @@ def test_tall_panel_path_vs_oracle(gp, kname, N, P):
     bad = dict(params, k_scale=-1.0)
     mean, cov = m.get_mvn_posterior(Xn, bad)
     assert np.isnan(mean).all() and np.isnan(cov).all()
+
+
+@pytest.mark.parametrize("N", [300, 2500])
+def test_factor_cache_reuse_with_more_and_fewer_test_points(gp, N):
+    """Single-theta calls keep the factor of k_XX (the reference re-inverts it per call, gp.py:269-271).  The right-hand
+    sides live under the factor in the same buffer, so a later call with MORE test points has to grow the buffer around
+    the factor; at N >= 2048 the reuse solves through the kept inverses of the diagonal blocks (trsm_tall).  Each reuse
+    is checked against the oracle, for a handful and for many test points."""
+    import ctypes
+    rng = np.random.default_rng(N)
+    d = 2
+    X = rng.uniform(0, 1, (N, d))
+    y = np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1]) + 0.1 * rng.standard_normal(N)
+    params = {"k_length": np.array([0.3, 0.4]), "k_scale": 1.2, "noise": 0.05}
+    m = gp.ExactGP(d, "Matern")
+    m.X_train, m.y_train = X, y
+    hits = m.ctx.lib.b2gp_debug_cache_hits
+    hits.restype, hits.argtypes = ctypes.c_int64, [ctypes.c_void_p]
+    m.ctx.set_option("drop_factor_cache", 1)
+    cond = np.linalg.cond(oracle.get_kernel("Matern")(X, X, params, params["noise"]))
+    tol = RTOL * max(1.0, cond / 1e5)
+    h0 = hits(m.ctx.h)
+    for k, P in enumerate((40, 10, 700, 1500, 3)):            # the first call factors, the others reuse; 700 and 1500 grow the buffer
+        Xn = rng.uniform(0, 1, (P, d))
+        mean, cov = m.get_mvn_posterior(Xn, params)
+        rmean, rcov = oracle.exact_posterior_chol(X, y, Xn, params, "Matern")
+        assert_close(mean, rmean, tol, f"mean call {k} P={P} cond={cond:.1e}")
+        assert_close(cov, rcov, tol, f"cov call {k} P={P} cond={cond:.1e}")
+        assert hits(m.ctx.h) - h0 == k
