@@ -292,6 +292,24 @@ class ExactGP:
         if print_summary:
             self._print_summary()
 
+    def sample_from_prior(self, rng_key, X, num_samples: int = 10) -> np.ndarray:
+        """gp.py:401-408: samples [num_samples, N] from the prior predictive at X -- hyper-parameters (and mean-function
+        parameters) drawn from their priors, y ~ N(mean_fn(X), k(X, X) + (noise + jitter) I) per draw.  The Gram matrices
+        are built and the draws made on the device (kernel call, b2gp_mvn_sample); the key seeds NumPy's generator (the
+        distribution is the reference's, NumPyro's own key stream is not reproduced)."""
+        from .inference import prior_draws
+        from .utils import seed_from_key
+        X = np.asarray(self._set_data(X), dtype=np.float64)
+        N, S = X.shape[0], int(num_samples)
+        rng = seed_from_key(rng_key)
+        K, mean = np.empty((S, N, N)), np.zeros((S, N))
+        for s, (kp, noise, mp) in enumerate(prior_draws(self, rng, S, X.shape[1])):
+            K[s] = np.asarray(self.kernel(X, X, kp, noise), dtype=np.float64)              # gp.py:157
+            if self.mean_fn is not None:                                                    # gp.py:150-155
+                mean[s] = np.asarray(self.mean_fn(X, mp) if mp is not None else self.mean_fn(X), dtype=np.float64).squeeze()
+        y, _ = self.ctx.mvn_sample(mean, K, rng.standard_normal((S, 1, N)))
+        return y[:, 0, :]
+
     def _print_summary(self):
         samples = self.get_samples(1)
         for k, v in samples.items():

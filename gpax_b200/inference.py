@@ -92,6 +92,33 @@ class LogJoint:
         return out
 
 
+def gp_model_program(m, d, kind):
+    """the host side of ExactGP.model (gp.py:137-154): every statement except the likelihood.  Runs under
+    priors.run_program; returns (kernel-parameter dict, noise, mean-function parameter dict or None)."""
+    if m.kernel_prior is not None:
+        kp = m.kernel_prior()
+    else:                                                              # gp.py:229-247
+        lp = m.lengthscale_prior_dist or P.LogNormal(0.0, 1.0)
+        with P.plate("ard", d):
+            length = P.sample("k_length", lp)
+        kp = {"k_length": length, "k_scale": P.sample("k_scale", P.LogNormal(0.0, 1.0))}
+        if kind == "Periodic":
+            kp["period"] = P.sample("period", P.LogNormal(0.0, 1.0))
+    if m.noise_prior is not None:
+        noise = m.noise_prior()
+    else:                                                              # gp.py:222-227
+        noise = P.sample("noise", m.noise_prior_dist or P.LogNormal(0.0, 1.0))
+    mp = m.mean_fn_prior() if (m.mean_fn is not None and m.mean_fn_prior is not None) else None
+    return kp, noise, mp
+
+
+def prior_draws(model, rng, num_samples, d):
+    """`num_samples` runs of the model's prior statements with every site drawn from its prior (what NumPyro's Predictive
+    does for gp.py:401-408): list of (kernel params, noise, mean params)"""
+    kind = model.kernel_name if isinstance(model.kernel_name, str) else None
+    return [P.run_program(lambda: gp_model_program(model, d, kind), rng=rng)[0] for _ in range(int(num_samples))]
+
+
 class ProgramLogJoint:
     """The log joint of ExactGP.model (gp.py:137-164) when some of its priors are *programs*: `kernel_prior()` returning
     the kernel-parameter dict (gp.py:141-142), the deprecated `noise_prior()` (gp.py:146-147), `mean_fn_prior()` feeding a
@@ -131,24 +158,8 @@ class ProgramLogJoint:
         _, sites2, _ = P.run_program(self._model_program, vals)
         self.hierarchical = any(vars(sites[k].prior) != vars(sites2[k].prior) for k in sites)
 
-    # the host side of gp.py:137-154 (everything except the likelihood statement)
     def _model_program(self):
-        m = self.m
-        if m.kernel_prior is not None:
-            kp = m.kernel_prior()
-        else:                                                              # gp.py:229-247
-            lp = m.lengthscale_prior_dist or P.LogNormal(0.0, 1.0)
-            with P.plate("ard", self.d):
-                length = P.sample("k_length", lp)
-            kp = {"k_length": length, "k_scale": P.sample("k_scale", P.LogNormal(0.0, 1.0))}
-            if self.kind == "Periodic":
-                kp["period"] = P.sample("period", P.LogNormal(0.0, 1.0))
-        if m.noise_prior is not None:
-            noise = m.noise_prior()
-        else:                                                              # gp.py:222-227
-            noise = P.sample("noise", m.noise_prior_dist or P.LogNormal(0.0, 1.0))
-        mp = m.mean_fn_prior() if self.has_mean_params else None
-        return kp, noise, mp
+        return gp_model_program(self.m, self.d, self.kind)
 
     def _run(self, u):
         """u -> (theta[d+3], mean vector or None, sites with values)"""

@@ -243,8 +243,9 @@ class Site:
 
 
 class _Run:
-    def __init__(self, values):
+    def __init__(self, values, rng=None):
         self.values = values or {}
+        self.rng = rng
         self.sites = OrderedDict()
         self.plates = []
         self.deterministic = OrderedDict()
@@ -273,6 +274,8 @@ def sample(name, fn, obs=None, rng_key=None, sample_shape=()):
         v = np.asarray(run.values[name], dtype=np.float64)
         if v.shape != shape:
             v = np.broadcast_to(v, shape) * 1.0
+    elif run.rng is not None:
+        v = np.asarray(fn.sample(run.rng, shape), dtype=np.float64)        # prior draw (numpyro's Predictive / seed handler)
     else:
         v = np.full(shape, float(fn.median()))
     v = v if shape else float(v)
@@ -301,10 +304,11 @@ class plate:
         return False
 
 
-def run_program(fn, values=None):
-    """run `fn()` with its sample sites substituted from `values` (name -> array); returns (fn's result, sites, deterministics)"""
+def run_program(fn, values=None, rng=None):
+    """run `fn()` with its sample sites substituted from `values` (name -> array); sites without a value are set to their
+    prior median, or -- with a numpy Generator `rng` -- drawn from their prior.  Returns (fn's result, sites, deterministics)"""
     prev = getattr(_tls, "run", None)
-    _tls.run = run = _Run(values)
+    _tls.run = run = _Run(values, rng)
     try:
         out = fn()
     finally:

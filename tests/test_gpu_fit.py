@@ -303,3 +303,25 @@ def test_vigp_fit_with_prob_mean_fn():
     assert {"a", "b"} <= set(m.kernel_params)
     mean, var = m.predict(0, X)
     assert mean.shape == X.shape and (var > 0).all() and m.svi.losses[-10:].mean() < m.svi.losses[:10].mean()
+
+
+def test_sample_from_prior():
+    """tests/test_gp.py:333-338 contract + the draws have the prior-predictive variance"""
+    import gpax_b200
+    from gpax_b200 import priors as P
+    X, _ = _dummy_data()
+    m = gpax_b200.ExactGP(1, "RBF")
+    y = m.sample_from_prior(0, X, num_samples=8)
+    assert y.shape == (8, X.shape[0]) and np.isfinite(y).all()
+    np.testing.assert_array_equal(y, m.sample_from_prior(0, X, num_samples=8))       # same key, same draws
+    # narrow priors: Var y_i = k_scale + noise + jitter, Cov(y_i, y_j) = k_scale exp(-0.5 (x_i - x_j)^2 / l^2)
+    tight = lambda v: P.LogNormal(np.log(v), 1e-3)                                     # noqa: E731
+    def kp():
+        return {"k_length": P.sample("k_length", tight(0.5)), "k_scale": P.sample("k_scale", tight(2.0))}
+    with pytest.warns(UserWarning):
+        m2 = gpax_b200.ExactGP(1, "RBF", kernel_prior=kp, noise_prior_dist=tight(0.3), mean_fn=lambda x: 3.0 * x.squeeze())
+    Xg = np.array([0.0, 0.25, 2.0])
+    ys = m2.sample_from_prior(1, Xg, num_samples=6000)
+    C = np.cov(ys.T)
+    want = 2.0 * np.exp(-0.5 * (Xg[:, None] - Xg[None]) ** 2 / 0.25) + 0.3 * np.eye(3)
+    assert np.abs(C - want).max() < 0.15 and np.abs(ys.mean(0) - 3.0 * Xg).max() < 0.08

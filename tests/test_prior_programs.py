@@ -149,3 +149,26 @@ def test_program_errors():
         numpyro.run_program(twice)
     with pytest.raises(TypeError):
         numpyro.run_program(lambda: numpyro.sample("a", object()))
+
+
+def test_prior_draws_follow_the_priors():
+    """sample_from_prior's host half (gp.py:401-408): every site drawn from its prior, programs included"""
+    from gpax_b200.inference import prior_draws
+    m = ExactGP(2, "Periodic", lengthscale_prior_dist=numpyro.Gamma(2, 5), noise_prior_dist=numpyro.HalfNormal(0.1))
+    dr = prior_draws(m, np.random.default_rng(1), 4000, 2)
+    ell = np.array([kp["k_length"] for kp, _, _ in dr])
+    noise = np.array([n for _, n, _ in dr])
+    period = np.array([kp["period"] for kp, _, _ in dr])
+    assert ell.shape == (4000, 2) and abs(ell.mean() - 0.4) < 0.02            # Gamma(2, 5): mean 0.4
+    assert abs(noise.mean() - 0.1 * np.sqrt(2 / np.pi)) < 0.005               # HalfNormal(0.1)
+    assert abs(np.median(period) - 1.0) < 0.08                                 # LogNormal(0, 1): median 1
+    m2 = ExactGP(1, "RBF", mean_fn=dummy_mean_fn, mean_fn_prior=dummy_mean_fn_priors, kernel_prior=hierarchical_prior_1d)
+    kp, noise, mp = prior_draws(m2, np.random.default_rng(2), 1, 1)[0]
+    assert set(mp) == {"a", "b"} and kp["k_scale"] > 0 and np.shape(kp["k_length"]) == (1,)
+
+
+def hierarchical_prior_1d():
+    top = numpyro.sample("top", numpyro.distributions.LogNormal(0, 0.5))
+    with numpyro.plate("ard", 1):
+        length = numpyro.sample("k_length", numpyro.distributions.LogNormal(np.log(top), 0.3))
+    return {"k_length": length, "k_scale": 2.0 * top}
