@@ -40,11 +40,13 @@ class Prior:
         c.shape = tuple(int(b) for b in batch_shape)
         return c
 
-    def transform(self, u):            # theta(u)
-        return np.exp(u)
+    def transform(self, u):            # theta(u); a leapfrog step far out may overflow to inf, which the log joint rejects
+        with np.errstate(over="ignore"):
+            return np.exp(u)
 
     def dtheta_du(self, u):
-        return np.exp(u)
+        with np.errstate(over="ignore"):
+            return np.exp(u)
 
     def log_abs_jac(self, u):          # log |dtheta/du|
         return u
