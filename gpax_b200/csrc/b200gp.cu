@@ -1394,7 +1394,7 @@ static int mll_impl(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const d
     if (noise_vec) RET_IF(stage_in(ctx, st, ctx->d_in[6], noise_vec, (size_t)N * 8, dev, &dnv));
     const int64_t ld = round_up(N, 8);
     const int64_t tiles = ceil_div(N, MLL_TILE);
-    RET_IF(ensure(ctx, sl.A, (size_t)N * ld * 8));
+    RET_IF(ensure(ctx, sl.A, (size_t)(N + 1) * ld * 8));
     RET_IF(ensure(ctx, sl.Linv, (size_t)linv_bytes(N)));
     RET_IF(ensure(ctx, ctx->d_info, 64));
     RET_IF(ensure(ctx, sl.misc, (size_t)(3 * ld + 64 + tiles * tiles * nth) * 8));
@@ -1402,8 +1402,8 @@ static int mll_impl(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const d
     CUDA_TRY(ctx, cudaMemsetAsync(dinfo, 0, 8, st));
     double* A = (double*)sl.A.p;
     double* Linv = (double*)sl.Linv.p;
-    double* w = (double*)sl.misc.p;      // L^{-1} y
-    double* alpha = w + ld;              // K^{-1} y
+    double* w = A + N * ld;              // y rides under K as a right-hand-side row: L^{-1} y after the factorisation
+    double* alpha = (double*)sl.misc.p + ld;   // K^{-1} y
     double* sc = alpha + ld;             // [0] sum log L_ii, [1] |w|^2, [8..8+nth) grad
     double* partial = sc + 64;
     RET_IF(launch_gram(ctx, st, kind, dX, N, dX, N, d, dth, 1.0, jitter, 1, 1, A, ld));
@@ -1412,9 +1412,10 @@ static int mll_impl(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const d
         CUDA_TRY(ctx, cudaGetLastError());
         ctx->launches++;
     }
-    RET_IF(potrf_rec(ctx, st, A, ld, N, Linv, dinfo, 0));
     CUDA_TRY(ctx, cudaMemcpyAsync(w, dy, (size_t)N * 8, cudaMemcpyDeviceToDevice, st));
-    RET_IF(trsm_rec(ctx, st, w, ld, 1, A, ld, N, Linv));
+    // the scheme of the posterior (tall-panel int8 at N >= 2048); w = L^{-1} y falls out of the panel solves instead of
+    // a separate chain of 2 N / 128 strip launches for one row
+    RET_IF(potrf_auto(ctx, st, A, ld, N, 1, Linv, dinfo));
     logdiag_kernel<<<1, 256, 0, st>>>(A, ld, N, sc);
     rowdot2_kernel<<<1, RD_THREADS, 0, st>>>(w, ld, N, nullptr, 1.0, nullptr, sc + 1);
     CUDA_TRY(ctx, cudaGetLastError());
@@ -1432,7 +1433,9 @@ static int mll_impl(b2gp_ctx* ctx, int kind, const double* X, int64_t N, const d
         if (grad) {
             RET_IF(ensure(ctx, sl.Vt, (size_t)N * ld * 8));
             double* Kinv = (double*)sl.Vt.p;
-            RET_IF(gemm_nt(ctx, st, N, N, N, 1.0, Bt, ld, Bt, ld, 0.0, Kinv, ld, true));
+            // K^{-1} = L^{-T} L^{-1} accumulated onto zeros: beta = 1 is what the int8 tensor-core path takes (7 planes here)
+            CUDA_TRY(ctx, cudaMemsetAsync(Kinv, 0, (size_t)N * ld * 8, st));
+            RET_IF(gemm_nt(ctx, st, N, N, N, 1.0, Bt, ld, Bt, ld, 1.0, Kinv, ld, true));
             dim3 g((unsigned)tiles, (unsigned)tiles);
             mll_grad_kernel<<<g, MLL_THREADS, 0, st>>>(dX, N, d, kind, dth, alpha, Kinv, ld, partial);
             mll_finish_kernel<<<1, 32, 0, st>>>(partial, tiles * tiles, nth, sc + 8);

@@ -19,7 +19,7 @@ def mll_ref(kind, X, y, theta, jitter):
     return -0.5 * w @ w - np.log(np.diag(L)).sum() - 0.5 * len(y) * np.log(2 * np.pi)
 
 
-@pytest.mark.parametrize("kind,d,N", [("RBF", 1, 50), ("Matern", 2, 300), ("Periodic", 1, 130), ("RBF", 3, 700)])
+@pytest.mark.parametrize("kind,d,N", [("RBF", 1, 50), ("Matern", 2, 300), ("Periodic", 1, 130), ("RBF", 3, 700), ("Matern", 2, 2300)])
 def test_mll_value_and_gradient(kind, d, N):
     import gpax_b200
     ctx = gpax_b200.default_context()
